@@ -1,0 +1,136 @@
+// K1 -- materialised cost-functor evaluation (residuals + per-parameter-block
+// Jacobians in the Ceres CostFunction::Evaluate layout), and K6's cost-only
+// evaluation used for the LM gain ratio.
+//
+// One thread per tag corner (4 threads = one observation block); each thread
+// writes its two residual rows of every Jacobian block as 16-byte vector
+// stores.  The kernel is HBM-write-bound: 1 408 B out per 72 B in.
+#include "common.cuh"
+#include "kernels.h"
+#include "model.cuh"
+
+namespace rcc {
+
+constexpr int EVAL_THREADS = 256;
+
+int eval_grid(int64_t n) { return ceil_div(n * 4, EVAL_THREADS); }
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  }
+  return s;  // valid on thread 0
+}
+
+template <bool RIG, bool WANT_J>
+__global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a) {
+  __shared__ double red[EVAL_THREADS / 32];
+  const int64_t tid = (int64_t)blockIdx.x * EVAL_THREADS + threadIdx.x;
+  const int64_t g = tid >> 2;
+  const int t = (int)(tid & 3);
+  double r2 = 0.0;
+  if (g < a.n) {
+    const int vi = a.view_idx[g], mi = a.marker_idx[g], cam = a.cam[g];
+    constexpr int SP = RIG ? 15 : 9;
+    BlockGeom<RIG> geo;
+    block_geometry<RIG>(a.view_x + (size_t)vi * POSEX, a.marker_x + (size_t)mi * POSEX,
+                        RIG ? a.ext_x + (size_t)cam * POSEX : nullptr, geo);
+    double ox, oy;
+    corner_xy(t, 0.5 * a.sizes[mi], ox, oy);
+    const double2 px = *reinterpret_cast<const double2*>(a.pix + g * 8 + 2 * t);
+    CornerRows<RIG> c;
+    eval_corner<RIG, WANT_J>(geo, a.shared + (size_t)cam * SP, ox, oy, px.x, px.y, c);
+    if (!(c.depth > 0.0) || !isfinite(c.r[0]) || !isfinite(c.r[1])) *a.fail_flag = 1;
+    r2 = c.r[0] * c.r[0] + c.r[1] * c.r[1];
+    const int64_t o = a.orig ? (int64_t)a.orig[g] : g;
+    if (a.residuals) *reinterpret_cast<double2*>(a.residuals + o * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
+    if (WANT_J) {
+      if (a.jac_intr) {
+        double2* d = reinterpret_cast<double2*>(a.jac_intr + o * 32 + 8 * t);
+        d[0] = make_double2(c.js[0][0], c.js[0][1]);
+        d[1] = make_double2(c.js[0][2], c.js[0][3]);
+        d[2] = make_double2(c.js[1][0], c.js[1][1]);
+        d[3] = make_double2(c.js[1][2], c.js[1][3]);
+      }
+      if (a.jac_dist) {
+        double2* d = reinterpret_cast<double2*>(a.jac_dist + o * 40 + 10 * t);
+        d[0] = make_double2(c.js[0][4], c.js[0][5]);
+        d[1] = make_double2(c.js[0][6], c.js[0][7]);
+        d[2] = make_double2(c.js[0][8], c.js[1][4]);
+        d[3] = make_double2(c.js[1][5], c.js[1][6]);
+        d[4] = make_double2(c.js[1][7], c.js[1][8]);
+      }
+      if (a.jac_view) {
+        double2* d = reinterpret_cast<double2*>(a.jac_view + o * 48 + 12 * t);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jv[i][2 * j], c.jv[i][2 * j + 1]);
+      }
+      if (a.jac_marker) {
+        double2* d = reinterpret_cast<double2*>(a.jac_marker + o * 48 + 12 * t);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jm[i][2 * j], c.jm[i][2 * j + 1]);
+      }
+      if (RIG && a.jac_ext) {
+        double2* d = reinterpret_cast<double2*>(a.jac_ext + o * 48 + 12 * t);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jx[i][2 * j], c.jx[i][2 * j + 1]);
+      }
+    }
+  }
+  const double s = block_sum(r2, red);
+  if (threadIdx.x == 0 && a.cost2_partials) a.cost2_partials[blockIdx.x] = s;
+}
+
+void launch_evaluate(bool rig, bool want_jac, const EvalArgs& a, cudaStream_t s) {
+  if (a.n == 0) return;
+  const int grid = eval_grid(a.n);
+  if (rig) {
+    if (want_jac) evaluate_kernel<true, true><<<grid, EVAL_THREADS, 0, s>>>(a);
+    else evaluate_kernel<true, false><<<grid, EVAL_THREADS, 0, s>>>(a);
+  } else {
+    if (want_jac) evaluate_kernel<false, true><<<grid, EVAL_THREADS, 0, s>>>(a);
+    else evaluate_kernel<false, false><<<grid, EVAL_THREADS, 0, s>>>(a);
+  }
+  RCC_CUDA(cudaGetLastError());
+}
+
+void launch_cost(bool rig, const EvalArgs& a, cudaStream_t s) {
+  EvalArgs b = a;
+  b.residuals = nullptr;
+  b.jac_intr = b.jac_dist = b.jac_view = b.jac_marker = b.jac_ext = nullptr;
+  launch_evaluate(rig, false, b, s);
+}
+
+// deterministic single-CTA sum
+__global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ in, int64_t n, double* __restrict__ out,
+                                                   double scale) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s += in[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0] * scale;
+}
+
+void launch_sum(const double* in, int64_t n, double* out, double scale, cudaStream_t s) {
+  sum_kernel<<<1, 1024, 0, s>>>(in, n, out, scale);
+  RCC_CUDA(cudaGetLastError());
+}
+
+}  // namespace rcc

@@ -1,0 +1,263 @@
+// Internal interface between the host-side problem object (problem.cu) and the
+// CUDA kernels (assemble.cu, evaluate.cu, schur.cu).  Not part of the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rcc {
+
+// ---------------------------------------------------------------------------
+// Tile-pass geometry of the fused linearise+assemble kernel (K2).
+//
+// One staged Jacobian row holds the column groups
+//   O  (6)  d r / d own block      (the block the pass is segmented by)
+//   T  (6)  d r / d other block
+//   S1 (6)  d r / d (fx fy cx cy k1 k2)
+//   S2 (6)  d r / d (p1 p2 k3) | r | 0 | 0
+//   X  (6)  d r / d body_T_cam           (rig only)
+// and every lane of a thread-group owns one 6x6 product tile  I^T J  of two
+// column groups, accumulated over the 8 residual rows of each observation
+// block and over all blocks of its segment chunk.
+// ---------------------------------------------------------------------------
+enum Group : int { G_O = 0, G_T = 1, G_S1 = 2, G_S2 = 3, G_X = 4, G_NONE = 7 };
+
+template <bool RIG>
+struct PassGeom {
+  static constexpr int TPB = RIG ? 8 : 5;     // tiles (= lanes) per observation block
+  static constexpr int BPW = RIG ? 4 : 6;     // observation blocks per warp iteration
+  static constexpr int NCOL = RIG ? 30 : 24;  // doubles per staged row
+  static constexpr int BLK_STRIDE = 8 * NCOL + 2;  // +2 doubles: de-phase the blocks across banks
+  static constexpr int WARP_SMEM = (BPW * BLK_STRIDE > 36 * 32) ? BPW * BLK_STRIDE : 36 * 32;  // doubles
+  static constexpr int SP = RIG ? 15 : 9;     // shared parameters per camera
+  static constexpr int WARPS = 4;             // warps (= chunks) per CTA
+};
+
+// tile tables: (I group, J group) of tile t in the E pass / F pass
+__host__ __device__ constexpr int tile_I(bool rig, bool epass, int t) {
+  if (!rig) {
+    if (epass) return t < 4 ? G_O : G_S1;                  // OO OT OS1 OS2 S1S1
+    return t < 3 ? G_O : (t == 3 ? G_S1 : G_S2);           // OO OS1 OS2 S1S2 S2S2
+  }
+  if (epass) return t < 5 ? G_O : (t < 7 ? G_S1 : G_X);    // OO OT OS1 OS2 OX S1S1 S1X XX
+  return t < 4 ? G_O : (t == 4 ? G_S1 : (t < 7 ? G_S2 : G_NONE));  // OO OS1 OS2 OX S1S2 S2S2 S2X -
+}
+__host__ __device__ constexpr int tile_J(bool rig, bool epass, int t) {
+  if (!rig) {
+    if (epass) return t == 0 ? G_O : (t == 1 ? G_T : (t == 2 ? G_S1 : (t == 3 ? G_S2 : G_S1)));
+    return t == 0 ? G_O : (t == 1 ? G_S1 : (t == 2 ? G_S2 : (t == 3 ? G_S2 : G_S2)));
+  }
+  if (epass)
+    return t == 0 ? G_O : (t == 1 ? G_T : (t == 2 ? G_S1 : (t == 3 ? G_S2 : (t == 4 ? G_X : (t == 5 ? G_S1 : G_X)))));
+  return t == 0 ? G_O : (t == 1 ? G_S1 : (t == 2 ? G_S2 : (t == 3 ? G_X : (t == 4 ? G_S2 : (t == 5 ? G_S2 : (t == 6 ? G_X : G_NONE))))));
+}
+
+// one chunk of a pass: `count` consecutive sorted observation blocks that share
+// the own block index and the camera
+struct Chunk {
+  int32_t own;
+  int32_t cam;
+  int32_t start;
+  int32_t count;
+};
+
+struct AssembleArgs {
+  // sorted observation blocks of this pass
+  const int32_t* oth;     // [n] index of the other 6-dof block
+  const double* pix;      // [n*8]
+  const Chunk* chunks;    // [n_chunks]
+  int32_t n_chunks;
+  // parameters
+  const double* view_x;   // expanded poses [n_views*24]
+  const double* marker_x; // [n_markers*24]
+  const double* ext_x;    // [n_cam*24] (rig)
+  const double* shared;   // [n_cam*SP]
+  const double* sizes;    // [n_markers]
+  // outputs
+  double* partials;       // [n_chunks * TPB * 36]
+  double* W;              // [n*36] (E pass only) row-major 6x6: rows own, cols other
+  int32_t* fail_flag;     // set to 1 on depth <= 0 / non-finite residual
+};
+
+// K2: fused residual + Jacobian + J^T J tiles.  own_is_view tells which pose
+// table the segment owner indexes.
+void launch_assemble(bool rig, bool epass, bool own_is_view, const AssembleArgs& a, cudaStream_t s);
+
+// per-own-block reduction of the chunk partials
+struct FinalizeSideArgs {
+  const double* partials;
+  const Chunk* chunks;
+  const int32_t* chunk_ptr;  // [n_own+1] chunks of own block i
+  int32_t n_own;
+  int32_t n_shared;          // n_cam * SP
+  double* Hoo;               // [n_own*36]
+  double* go;                // [n_own*6]
+  double* Hos;               // [n_own*6*n_shared]  (zeroed by the kernel)
+};
+void launch_finalize_side(bool rig, bool epass, const FinalizeSideArgs& a, cudaStream_t s);
+
+// per-camera reduction of the shared x shared tiles, gradient and cost
+struct FinalizeSharedArgs {
+  const double* part_e;
+  const double* part_f;
+  const int32_t* cam_chunks_e;  // chunk ids grouped by camera
+  const int32_t* cam_ptr_e;     // [n_cam+1]
+  const int32_t* cam_chunks_f;
+  const int32_t* cam_ptr_f;
+  int32_t n_cam;
+  int32_t n_shared;
+  double* Hss;                  // [n_shared*n_shared] block diagonal (zeroed by the kernel)
+  double* gs;                   // [n_shared]
+  double* cost2_cam;            // [n_cam] sum r^2 per camera
+};
+void launch_finalize_shared(bool rig, const FinalizeSharedArgs& a, cudaStream_t s);
+
+// pose expansion: rvec,t -> R, Jr, t
+void launch_expand_poses(const double* views, int n_views, double* view_x, const double* markers, int n_markers,
+                         double* marker_x, const double* shared, int n_cam, int sp, double* ext_x, cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// K1 / K6: materialised evaluation and cost-only evaluation
+// ---------------------------------------------------------------------------
+struct EvalArgs {
+  int64_t n;
+  const int32_t* view_idx;  // [n] per sorted block
+  const int32_t* marker_idx;
+  const int32_t* cam;
+  const int32_t* orig;      // caller position of sorted block
+  const double* pix;
+  const double* view_x;
+  const double* marker_x;
+  const double* ext_x;
+  const double* shared;
+  const double* sizes;
+  // outputs (caller order; any may be null)
+  double* residuals;        // [n*8]
+  double* jac_intr;         // [n*8*4]
+  double* jac_dist;         // [n*8*5]
+  double* jac_view;         // [n*8*6]
+  double* jac_marker;       // [n*8*6]
+  double* jac_ext;          // [n*8*6]
+  double* cost2_partials;   // [grid] sum r^2 per CTA
+  int32_t* fail_flag;
+};
+int eval_grid(int64_t n);   // CTAs launch_evaluate / launch_cost will use
+void launch_evaluate(bool rig, bool want_jac, const EvalArgs& a, cudaStream_t s);
+void launch_cost(bool rig, const EvalArgs& a, cudaStream_t s);
+// deterministic sum of n doubles -> out[0] (single CTA)
+void launch_sum(const double* in, int64_t n, double* out, double scale, cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// K3: Schur complement
+// ---------------------------------------------------------------------------
+struct SchurPrepArgs {
+  int32_t n_e;
+  int32_t n_shared;
+  int32_t n_bb;                  // border blocks per E block: ceil((n_shared+1)/6)
+  const double* Hee;             // [n_e*36]
+  const double* ge;              // [n_e*6]
+  const double* Hes;             // [n_e*6*n_shared]
+  const uint8_t* e_const;        // [n_e]
+  const int32_t* row_ptr;        // [n_e+1] pairs of row e
+  const int32_t* pair_mptr;      // [n_pairs+1]
+  const int32_t* pair_members;   // sorted-observation positions
+  const double* W;               // [n_obs*36]
+  double radius, min_diag, max_diag;
+  double* Linv;                  // [n_e*36] row-major lower-triangular inverse of chol(Hee + D)
+  double* Y;                     // [n_pairs*36] column-major 6x6 blocks  L^-1 W
+  double* Yb;                    // [n_e*n_bb*36] column-major blocks L^-1 [Hes | ge | 0]
+  double* d2e;                   // [n_e*6] damping actually applied
+};
+void launch_schur_prep(const SchurPrepArgs& a, cudaStream_t s);
+
+struct SchurSyrkArgs {
+  int32_t n_f, n_e;
+  int32_t n_shared, n_bb;
+  int32_t tile_w;                // kept blocks per column tile
+  int32_t n_tiles;               // ceil(n_f / tile_w)
+  int32_t ld;                    // row stride of S
+  const int32_t* col_ptr;        // [n_f+1]
+  const int32_t* col_pair;       // pair ids of column f, ascending e
+  const int32_t* pair_e;         // [n_pairs]
+  const int32_t* pair_f;         // [n_pairs]
+  const int32_t* tile_ptr;       // [n_e*(n_tiles+1)]
+  const double* Y;
+  const double* Yb;
+  const double* Hff;             // [n_f*36]
+  const double* gf;              // [n_f*6]
+  const double* Hfs;             // [n_f*6*n_shared]
+  double* S;                     // [(n + extra rows) * ld]
+};
+void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s);
+
+struct SchurSharedArgs {
+  int32_t n_e, n_f, n_shared, n_bb, ld;
+  const double* Yb;
+  const double* Hss;
+  const double* gs;
+  double* scratch;               // [SHARED_SLICES * (6 n_bb)^2]
+  double* S;
+};
+constexpr int SHARED_SLICES = 128;
+void launch_schur_shared(const SchurSharedArgs& a, cudaStream_t s);
+
+// extra rows appended to S for the all-reduce: [hdiag (n) | gF (n) | scalars (8)]
+struct ReducedTailArgs {
+  int32_t n_f, n_shared, ld;
+  const double* Hff;
+  const double* gf;
+  const double* Hss;
+  const double* gs;
+  const double* cost2_cam;  // [n_cam]
+  int32_t n_cam;
+  double* S;                // tail starts at S + n*ld
+};
+void launch_reduced_tail(const ReducedTailArgs& a, cudaStream_t s);
+
+struct MaskArgs {
+  int32_t n, ld;
+  double radius, min_diag, max_diag;
+  const int32_t* const_idx;  // reduced-system indices held constant
+  int32_t n_const;
+  double* S;                 // damping added to the diagonal, constants masked
+  double* rhs;               // [n]  = -b  (solve S x = rhs)
+  double* d2f;               // [n] damping applied (0 on constants)
+  double* gF;                // [n] masked gradient copy
+};
+void launch_mask_damp(const MaskArgs& a, cudaStream_t s);
+
+struct BacksubArgs {
+  int32_t n_e, n_f, n_shared, n_bb;
+  const int32_t* row_ptr;
+  const int32_t* pair_f;
+  const double* Y;
+  const double* Yb;
+  const double* Linv;
+  const double* ge;
+  const double* d2e;
+  const double* delta_F;  // [6 n_f + n_shared]
+  const double* x_e;      // current E parameters [n_e*6]
+  const int32_t* e_count; // observations per E block on this rank
+  double* delta_e;        // [n_e*6]
+  double* partials;       // [n_e*4]: mcc, |d|^2, |x|^2, 0 per E block
+};
+void launch_backsub(const BacksubArgs& a, cudaStream_t s);
+
+// F-side model-cost-change / norms: out[0..2] = mcc_F, |dF|^2, |xF|^2
+void launch_f_stats(const double* gF, const double* d2f, const double* delta_F, const double* x_f, const double* x_s,
+                    int32_t n_f, int32_t n_shared, double* out3, cudaStream_t s);
+// reduce the per-E-block partials: out[0..2]
+void launch_e_stats(const double* partials, int32_t n_e, double* out3, cudaStream_t s);
+
+// x_new = x + delta (6-dof blocks and shared block)
+void launch_apply(const double* x, const double* d, double* out, int64_t n, cudaStream_t s);
+// make a symmetric full matrix out of the upper triangle (parity read-back only)
+void launch_symmetrize(double* S, int32_t n, int32_t ld, cudaStream_t s);
+// gather pixels from caller order into a sorted order
+void launch_permute_pixels(const double* src, const int32_t* orig, double* dst, int64_t n, cudaStream_t s);
+// write a scratch buffer (L2 flush)
+void launch_fill(double* p, int64_t n, double v, cudaStream_t s);
+// FP64 FMA throughput microbenchmark kernel; returns number of FMAs issued
+double launch_fp64_peak(int iters, cudaStream_t s);
+
+}  // namespace rcc

@@ -1,0 +1,96 @@
+// Host-side problem object behind the opaque C handle.
+#pragma once
+
+#include <cusolverDn.h>
+#include <nccl.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rcc {
+
+enum Stage : int {
+  ST_EXPAND = 0, ST_ASSEMBLE_E, ST_ASSEMBLE_F, ST_FINALIZE, ST_SCHUR_PREP, ST_SCHUR_SYRK, ST_SCHUR_SHARED,
+  ST_ALLREDUCE, ST_MASK, ST_CHOLESKY, ST_BACKSUB, ST_COST, ST_EVALUATE, ST_H2D, ST_COUNT
+};
+const char* stage_name(int s);
+
+struct StageTimer {
+  struct Pending { int stage; cudaEvent_t a, b; };
+  bool on = false;
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  double ms[ST_COUNT] = {0};
+  int64_t launches[ST_COUNT] = {0};
+  cudaEvent_t get();
+  void begin(int stage, cudaStream_t s);
+  void end(cudaStream_t s);
+  void collect();  // requires the stream to be synchronised
+  void reset();
+  ~StageTimer();
+};
+
+}  // namespace rcc
+
+struct rcc_ba_problem {
+  rcc_ba_options opt{};
+  bool rig = false;
+  int sp = 9, n_cam = 1, n_shared = 9;
+  bool elim_view = true;
+  int n_views = 0, n_markers = 0, n_e = 0, n_f = 0;
+  int n_bb = 2, n_red = 0, ld = 0;
+  int64_t n_obs = 0, n_pairs = 0;
+  int tile_w = 128, n_tiles = 1;
+  int n_chunks_e = 0, n_chunks_f = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launch_count = 0;
+
+  // parameters: current (x) and candidate (xc)
+  rcc::DBuf<double> views, markers, sizes, shared, views_c, markers_c, shared_c;
+  rcc::DBuf<double> view_x, marker_x, ext_x, view_xc, marker_xc, ext_xc;
+  bool expanded_valid = false;
+  std::vector<uint8_t> c_view, c_marker, c_intr, c_dist, c_ext;
+  bool const_dirty = true;
+
+  // observation blocks, E-sorted and F-sorted
+  rcc::DBuf<int32_t> e_own, e_oth, e_cam, e_orig, f_oth, f_orig, e_chunk_ptr, f_chunk_ptr;
+  rcc::DBuf<double> e_pix, f_pix, pix_staging;
+  rcc::DBuf<rcc::Chunk> e_chunks, f_chunks;
+  rcc::DBuf<int32_t> cam_chunks_e, cam_ptr_e, cam_chunks_f, cam_ptr_f;
+  rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, col_ptr, col_pair, tile_ptr, e_count;
+  rcc::DBuf<uint8_t> e_const;
+
+  // linearisation products
+  rcc::DBuf<double> part_e, part_f, W, Hee, ge, Hes, Hff, gf, Hfs, Hss, gs, cost2_cam;
+  // Schur / step
+  rcc::DBuf<double> Linv, Y, Yb, d2e, S, shared_scratch, rhs, d2f, gFm, delta_F, delta_e, bs_partials, stats;
+  rcc::DBuf<int32_t> const_idx, fail_flag;
+  int n_const = 0;
+  double radius_used = 0.0;
+  // evaluation outputs
+  rcc::DBuf<double> o_res, o_ji, o_jd, o_jv, o_jm, o_jx, cost_partials, scalar;
+
+  cusolverDnHandle_t solver = nullptr;
+  rcc::DBuf<double> potrf_work;
+  rcc::DBuf<int> dev_info;
+  int potrf_lwork = 0;
+
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1;
+
+  bool have_obs = false, linearized = false, schur_done = false, step_ready = false, cand_ready = false;
+  double min_diag = 1e-6, max_diag = 1e32;
+  rcc::StageTimer timer;
+  rcc::DBuf<double> flush_buf;
+
+  // pinned host scratch for small read-backs
+  double* h_pinned = nullptr;
+
+  ~rcc_ba_problem();
+};

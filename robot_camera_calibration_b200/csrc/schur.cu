@@ -1,0 +1,560 @@
+// K3 -- Schur complement of the Gauss-Newton normal equations: the eliminated
+// 6-dof blocks (E) are folded into the reduced system over the kept blocks (F)
+// and the shared intrinsics / distortion / rig-extrinsics border.
+//
+// Replaces the Schur eliminator that would run inside
+// Ceres for the reference's missing optimiser stage.
+//
+// With H_ee + D_e = L L^T per eliminated block,  Y_ef = L^-1 W_ef,
+// Yb_e = L^-1 [H_es | g_e]:
+//     S   = H_FF - sum_e Y_e^T Y_e          (block-sparse SYRK, upper triangle)
+//     b   = g_F  - sum_e Y_e^T (L^-1 g_e)   (carried as one more column of S)
+//     d_e = -L^-T ( L^-1 g_e + Y_e d_F )    (back-substitution)
+// Every 6-row block of S is owned by exactly one CTA per column tile and summed
+// in a fixed order: no FP64 atomics, bitwise reproducible.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rcc {
+
+// ---------------------------------------------------------------------------
+// schur_prep: one warp per eliminated block
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) schur_prep_kernel(const SchurPrepArgs a) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= a.n_e) return;
+  // every lane factors the 6x6 block redundantly (registers only)
+  double L[6][6], Li[6][6], d2[6];
+  const double* H = a.Hee + (size_t)e * 36;
+  const bool is_const = a.e_const[e] != 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double dg = H[i * 6 + i];
+    d2[i] = fmin(fmax(dg, a.min_diag), a.max_diag) / a.radius;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      L[i][j] = 0.0;
+      Li[i][j] = 0.0;
+    }
+  // Cholesky (lower)
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = H[j * 6 + j] + d2[j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    s = fmax(s, 1e-300);
+    const double ljj = sqrt(s);
+    L[j][j] = ljj;
+    const double inv = 1.0 / ljj;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = H[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
+  }
+  // inverse of the lower-triangular factor (forward substitution per column)
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+#pragma unroll
+    for (int i = c; i < 6; ++i) {
+      double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = c; k < i; ++k) v -= L[i][k] * Li[k][c];
+      Li[i][c] = v / L[i][i];
+    }
+  }
+  if (is_const) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      d2[i] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) Li[i][j] = 0.0;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      a.d2e[(size_t)e * 6 + i] = d2[i];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) a.Linv[(size_t)e * 36 + i * 6 + j] = Li[i][j];
+    }
+  }
+  // Y = L^-1 * (sum of the member W blocks) for every pair of row e
+  for (int p = a.row_ptr[e] + lane; p < a.row_ptr[e + 1]; p += 32) {
+    double Wm[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) Wm[i] = 0.0;
+    for (int m = a.pair_mptr[p]; m < a.pair_mptr[p + 1]; ++m) {
+      const double2* w = reinterpret_cast<const double2*>(a.W + (size_t)a.pair_members[m] * 36);
+#pragma unroll
+      for (int i = 0; i < 18; ++i) {
+        const double2 v = w[i];
+        Wm[2 * i] += v.x;
+        Wm[2 * i + 1] += v.y;
+      }
+    }
+    double* y = a.Y + (size_t)p * 36;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j <= k; ++j) v += Li[k][j] * Wm[j * 6 + c];
+        y[c * 6 + k] = v;  // column-major
+      }
+  }
+  // border: columns 0..n_shared-1 = H_es, column n_shared = g_e, rest zero
+  const int ncol = a.n_bb * 6;
+  for (int s = lane; s < ncol; s += 32) {
+    double v[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (s < a.n_shared) v[j] = a.Hes[((size_t)e * 6 + j) * a.n_shared + s];
+      else if (s == a.n_shared) v[j] = a.ge[(size_t)e * 6 + j];
+      else v[j] = 0.0;
+    }
+    double* y = a.Yb + ((size_t)e * a.n_bb + s / 6) * 36 + (s % 6) * 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j <= k; ++j) acc += Li[k][j] * v[j];
+      y[k] = acc;
+    }
+  }
+}
+
+void launch_schur_prep(const SchurPrepArgs& a, cudaStream_t s) {
+  if (a.n_e == 0) return;
+  schur_prep_kernel<<<ceil_div((int64_t)a.n_e * 32, 128), 128, 0, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// schur_syrk: CTA (f, J) owns the 6 x (6*tile_w) strip of S in block row f and
+// column tile J (J == n_tiles: the shared/rhs border).  It walks the pairs
+// (e, f) of column f; for each, every thread takes one column of one partner
+// block Y_ef' of row e and accumulates  Y_ef^T Y_ef'[:,c]  into the strip held
+// in shared memory.
+// ---------------------------------------------------------------------------
+constexpr int SYRK_THREADS = 384;
+constexpr int SYRK_BATCH = 32;
+
+__global__ void __launch_bounds__(SYRK_THREADS) schur_syrk_kernel(const SchurSyrkArgs a) {
+  extern __shared__ double sm[];
+  const int f = blockIdx.x;
+  const int J = blockIdx.y;
+  const int tile_of_f = f / a.tile_w;
+  if (J < tile_of_f) return;
+  const bool border = (J == a.n_tiles);
+  const int width = border ? a.n_bb * 6 : 6 * min(a.tile_w, a.n_f - J * a.tile_w);  // strip columns
+  const int wpad = width | 1;  // odd row stride (in doubles) to spread the 6 rows over banks
+  double* acc = sm;                       // [6][wpad]
+  double* yi = sm + 6 * wpad;             // [SYRK_BATCH][36]  staged Y_ef of the current batch
+  int* meta = reinterpret_cast<int*>(yi + SYRK_BATCH * 36);  // [SYRK_BATCH][2] partner range
+  const int tid = threadIdx.x;
+  for (int k = tid; k < 6 * wpad; k += SYRK_THREADS) acc[k] = 0.0;
+
+  const int c0 = a.col_ptr[f], c1 = a.col_ptr[f + 1];
+  const int colbase = J * a.tile_w;  // first kept block of this tile
+  for (int cb = c0; cb < c1; cb += SYRK_BATCH) {
+    const int nb = min(SYRK_BATCH, c1 - cb);
+    __syncthreads();
+    // stage metadata + Y_ef blocks of the batch
+    if (tid < nb) {
+      const int p = a.col_pair[cb + tid];
+      const int e = a.pair_e[p];
+      int lo, hi;
+      if (border) {
+        lo = e * a.n_bb;
+        hi = lo + a.n_bb;
+      } else {
+        const int* tp = a.tile_ptr + (size_t)e * (a.n_tiles + 1);
+        lo = (J == tile_of_f) ? p : tp[J];
+        hi = tp[J + 1];
+      }
+      meta[2 * tid] = lo;
+      meta[2 * tid + 1] = hi;
+    }
+    for (int k = tid; k < nb * 36; k += SYRK_THREADS) {
+      const int q = k / 36;
+      yi[k] = a.Y[(size_t)a.col_pair[cb + q] * 36 + (k - q * 36)];
+    }
+    __syncthreads();
+    const double* src = border ? a.Yb : a.Y;
+    for (int q = 0; q < nb; ++q) {
+      const int lo = meta[2 * q], hi = meta[2 * q + 1];
+      const double* Yi = yi + q * 36;  // column-major: Yi[r*6+k] = Y[k][r]
+      for (int idx = tid; idx < (hi - lo) * 6; idx += SYRK_THREADS) {
+        const int j = lo + idx / 6, c = idx % 6;
+        const double2* yp = reinterpret_cast<const double2*>(src + (size_t)j * 36 + c * 6);
+        const double2 y0 = yp[0], y1 = yp[1], y2 = yp[2];
+        const int col = border ? (j - lo) * 6 + c : (a.pair_f[j] - colbase) * 6 + c;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double* yr = Yi + r * 6;
+          double v = yr[0] * y0.x;
+          v = fma(yr[1], y0.y, v);
+          v = fma(yr[2], y1.x, v);
+          v = fma(yr[3], y1.y, v);
+          v = fma(yr[4], y2.x, v);
+          v = fma(yr[5], y2.y, v);
+          acc[r * wpad + col] += v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // S strip = base - acc   (upper triangle in block granularity)
+  const size_t row0 = (size_t)6 * f;
+  for (int k = tid; k < 6 * width; k += SYRK_THREADS) {
+    const int r = k / width, cl = k - r * width;
+    double base = 0.0;
+    int gc;
+    if (border) {
+      gc = 6 * a.n_f + cl;
+      if (gc >= a.ld) continue;
+      if (cl < a.n_shared) base = a.Hfs[((size_t)f * 6 + r) * a.n_shared + cl];
+      else if (cl == a.n_shared) base = a.gf[(size_t)f * 6 + r];
+    } else {
+      gc = 6 * colbase + cl;
+      if (gc < 6 * f) continue;
+      if (gc < 6 * f + 6) base = a.Hff[(size_t)f * 36 + r * 6 + (gc - 6 * f)];
+    }
+    a.S[(row0 + r) * a.ld + gc] = base - acc[r * wpad + cl];
+  }
+}
+
+void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s) {
+  if (a.n_f == 0) return;
+  const int wmax = max(a.tile_w * 6, a.n_bb * 6) | 1;
+  const size_t smem = (size_t)(6 * wmax + SYRK_BATCH * 36) * sizeof(double) + SYRK_BATCH * 2 * sizeof(int);
+  static size_t attr = 0;
+  if (smem > attr) {
+    RCC_CUDA(cudaFuncSetAttribute(schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  dim3 grid(a.n_f, a.n_tiles + 1);
+  schur_syrk_kernel<<<grid, SYRK_THREADS, smem, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// shared x shared corner:  H_ss - sum_e Yb_e^T Yb_e   (and the rhs of the border)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) schur_shared_partial_kernel(const SchurSharedArgs a) {
+  const int nb = a.n_bb * 6;
+  const int slice = blockIdx.x;
+  const int per = (a.n_e + SHARED_SLICES - 1) / SHARED_SLICES;
+  const int e0 = slice * per, e1 = min(a.n_e, e0 + per);
+  for (int o = threadIdx.x; o < nb * nb; o += blockDim.x) {
+    const int s1 = o / nb, s2 = o - s1 * nb;
+    double acc = 0.0;
+    if (s2 >= s1) {
+      for (int e = e0; e < e1; ++e) {
+        const double* y1 = a.Yb + ((size_t)e * a.n_bb + s1 / 6) * 36 + (s1 % 6) * 6;
+        const double* y2 = a.Yb + ((size_t)e * a.n_bb + s2 / 6) * 36 + (s2 % 6) * 6;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v = fma(y1[k], y2[k], v);
+        acc += v;
+      }
+    }
+    a.scratch[(size_t)slice * nb * nb + o] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) schur_shared_final_kernel(const SchurSharedArgs a) {
+  const int nb = a.n_bb * 6;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nb * nb) return;
+  const int s1 = o / nb, s2 = o - s1 * nb;
+  if (s1 >= a.n_shared || s2 < s1) return;
+  const int gc = 6 * a.n_f + s2;
+  if (gc >= a.ld) return;
+  double acc = 0.0;
+  for (int q = 0; q < SHARED_SLICES; ++q) acc += a.scratch[(size_t)q * nb * nb + o];
+  double base = 0.0;
+  if (s2 < a.n_shared) base = a.Hss[(size_t)s1 * a.n_shared + s2];
+  else if (s2 == a.n_shared) base = a.gs[s1];
+  a.S[((size_t)6 * a.n_f + s1) * a.ld + gc] = base - acc;
+}
+
+void launch_schur_shared(const SchurSharedArgs& a, cudaStream_t s) {
+  const int nb = a.n_bb * 6;
+  schur_shared_partial_kernel<<<SHARED_SLICES, 256, 0, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+  schur_shared_final_kernel<<<ceil_div(nb * nb, 256), 256, 0, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// tail rows of the reduced buffer (ride along in the all-reduce)
+// ---------------------------------------------------------------------------
+__global__ void reduced_tail_kernel(const ReducedTailArgs a) {
+  const int n = 6 * a.n_f + a.n_shared;
+  double* tail = a.S + (size_t)n * a.ld;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double hd, g;
+    if (i < 6 * a.n_f) {
+      const int f = i / 6, k = i - 6 * f;
+      hd = a.Hff[(size_t)f * 36 + k * 6 + k];
+      g = a.gf[i];
+    } else {
+      const int s = i - 6 * a.n_f;
+      hd = a.Hss[(size_t)s * a.n_shared + s];
+      g = a.gs[s];
+    }
+    tail[i] = hd;
+    tail[n + i] = g;
+  }
+  if (i == 0) {
+    double c2 = 0.0;
+    for (int c = 0; c < a.n_cam; ++c) c2 += a.cost2_cam[c];
+    tail[2 * n + 0] = c2;
+    for (int k = 1; k < 8; ++k) tail[2 * n + k] = 0.0;
+  }
+}
+
+void launch_reduced_tail(const ReducedTailArgs& a, cudaStream_t s) {
+  const int n = 6 * a.n_f + a.n_shared;
+  reduced_tail_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// LM damping of the kept blocks + constant-parameter mask + rhs extraction
+// ---------------------------------------------------------------------------
+__global__ void damp_kernel(const MaskArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const double* tail = a.S + (size_t)a.n * a.ld;
+  const double d2 = fmin(fmax(tail[i], a.min_diag), a.max_diag) / a.radius;
+  a.S[(size_t)i * a.ld + i] += d2;
+  a.d2f[i] = d2;
+  a.rhs[i] = -a.S[(size_t)i * a.ld + a.n];
+  a.gF[i] = tail[a.n + i];
+}
+
+__global__ void mask_kernel(const MaskArgs a) {
+  const int c = a.const_idx[blockIdx.x];
+  for (int k = threadIdx.x; k < a.n; k += blockDim.x) {
+    if (k < c) a.S[(size_t)k * a.ld + c] = 0.0;       // column part of the upper triangle
+    else if (k > c) a.S[(size_t)c * a.ld + k] = 0.0;  // row part
+  }
+  if (threadIdx.x == 0) {
+    a.S[(size_t)c * a.ld + c] = 1.0;
+    a.rhs[c] = 0.0;
+    a.d2f[c] = 0.0;
+    a.gF[c] = 0.0;
+  }
+}
+
+void launch_mask_damp(const MaskArgs& a, cudaStream_t s) {
+  damp_kernel<<<ceil_div(a.n, 256), 256, 0, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+  if (a.n_const > 0) {
+    mask_kernel<<<a.n_const, 256, 0, s>>>(a);
+    RCC_CUDA(cudaGetLastError());
+  }
+}
+
+// ---------------------------------------------------------------------------
+// back-substitution: one warp per eliminated block
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= a.n_e) return;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int p = a.row_ptr[e] + lane; p < a.row_ptr[e + 1]; p += 32) {
+    const double* y = a.Y + (size_t)p * 36;
+    const double* d = a.delta_F + (size_t)a.pair_f[p] * 6;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double dc = d[c];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = fma(y[c * 6 + k], dc, v[k]);
+    }
+  }
+  // border: shared columns times d_shared, plus the g_e column (coefficient 1)
+  const double* ds = a.delta_F + (size_t)6 * a.n_f;
+  for (int s = lane; s <= a.n_shared; s += 32) {
+    const double* y = a.Yb + ((size_t)e * a.n_bb + s / 6) * 36 + (s % 6) * 6;
+    const double dc = (s < a.n_shared) ? ds[s] : 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = fma(y[k], dc, v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if (lane == 0) {
+    const double* Li = a.Linv + (size_t)e * 36;
+    double mcc = 0.0, dn = 0.0, xn = 0.0;
+    const bool owned = a.e_count[e] > 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double d = 0.0;
+#pragma unroll
+      for (int k = i; k < 6; ++k) d += Li[k * 6 + i] * v[k];  // L^-T v
+      d = -d;
+      a.delta_e[(size_t)e * 6 + i] = d;
+      const double x = a.x_e[(size_t)e * 6 + i];
+      mcc += -0.5 * a.ge[(size_t)e * 6 + i] * d + 0.5 * a.d2e[(size_t)e * 6 + i] * d * d;
+      dn += d * d;
+      if (owned) xn += x * x;
+    }
+    a.partials[(size_t)e * 4 + 0] = mcc;
+    a.partials[(size_t)e * 4 + 1] = dn;
+    a.partials[(size_t)e * 4 + 2] = xn;
+    a.partials[(size_t)e * 4 + 3] = 0.0;
+  }
+}
+
+void launch_backsub(const BacksubArgs& a, cudaStream_t s) {
+  if (a.n_e == 0) return;
+  backsub_kernel<<<ceil_div((int64_t)a.n_e * 32, 128), 128, 0, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// small reductions (single CTA, fixed order)
+// ---------------------------------------------------------------------------
+__device__ void cta_sum3(double s0, double s1, double s2, double* out3) {
+  __shared__ double red[3][256];
+  red[0][threadIdx.x] = s0;
+  red[1][threadIdx.x] = s1;
+  red[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+      red[2][threadIdx.x] += red[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out3[0] = red[0][0];
+    out3[1] = red[1][0];
+    out3[2] = red[2][0];
+  }
+}
+
+__global__ void __launch_bounds__(256) f_stats_kernel(const double* gF, const double* d2f, const double* dF,
+                                                      const double* x_f, const double* x_s, int n_f, int n_shared,
+                                                      double* out3) {
+  const int n = 6 * n_f + n_shared;
+  double mcc = 0.0, dn = 0.0, xn = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const double d = dF[i];
+    const double x = (i < 6 * n_f) ? x_f[i] : x_s[i - 6 * n_f];
+    mcc += -0.5 * gF[i] * d + 0.5 * d2f[i] * d * d;
+    dn += d * d;
+    xn += x * x;
+  }
+  cta_sum3(mcc, dn, xn, out3);
+}
+
+void launch_f_stats(const double* gF, const double* d2f, const double* delta_F, const double* x_f, const double* x_s,
+                    int32_t n_f, int32_t n_shared, double* out3, cudaStream_t s) {
+  f_stats_kernel<<<1, 256, 0, s>>>(gF, d2f, delta_F, x_f, x_s, n_f, n_shared, out3);
+  RCC_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) e_stats_kernel(const double* partials, int n_e, double* out3) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int e = threadIdx.x; e < n_e; e += 256) {
+    s0 += partials[(size_t)e * 4 + 0];
+    s1 += partials[(size_t)e * 4 + 1];
+    s2 += partials[(size_t)e * 4 + 2];
+  }
+  cta_sum3(s0, s1, s2, out3);
+}
+
+void launch_e_stats(const double* partials, int32_t n_e, double* out3, cudaStream_t s) {
+  e_stats_kernel<<<1, 256, 0, s>>>(partials, n_e, out3);
+  RCC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+__global__ void apply_kernel(const double* __restrict__ x, const double* __restrict__ d, double* __restrict__ out,
+                             int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[i] + d[i];
+}
+void launch_apply(const double* x, const double* d, double* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  apply_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x, d, out, n);
+  RCC_CUDA(cudaGetLastError());
+}
+
+__global__ void symmetrize_kernel(double* S, int n, int ld) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // column
+  const int i = blockIdx.y;                             // row
+  if (j < n && j > i) S[(size_t)j * ld + i] = S[(size_t)i * ld + j];
+}
+void launch_symmetrize(double* S, int32_t n, int32_t ld, cudaStream_t s) {
+  dim3 grid(ceil_div(n, 256), n);
+  symmetrize_kernel<<<grid, 256, 0, s>>>(S, n, ld);
+  RCC_CUDA(cudaGetLastError());
+}
+
+__global__ void permute_pixels_kernel(const double* __restrict__ src, const int32_t* __restrict__ orig,
+                                      double* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one double2 per thread
+  if (i >= n * 4) return;
+  const int64_t g = i >> 2;
+  const int q = (int)(i & 3);
+  const double2 v = reinterpret_cast<const double2*>(src + (size_t)orig[g] * 8)[q];
+  reinterpret_cast<double2*>(dst + g * 8)[q] = v;
+}
+void launch_permute_pixels(const double* src, const int32_t* orig, double* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  permute_pixels_kernel<<<ceil_div(n * 4, 256), 256, 0, s>>>(src, orig, dst, n);
+  RCC_CUDA(cudaGetLastError());
+}
+
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill(double* p, int64_t n, double v, cudaStream_t s) {
+  fill_kernel<<<NUM_SMS_B200 * 8, 256, 0, s>>>(p, n, v);
+  RCC_CUDA(cudaGetLastError());
+}
+
+// FP64 FMA microbenchmark: 8 independent chains per thread
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;
+}
+static double* g_peak_sink = nullptr;
+double launch_fp64_peak(int iters, cudaStream_t s) {
+  if (!g_peak_sink) RCC_CUDA(cudaMalloc(&g_peak_sink, 8));
+  const int grid = NUM_SMS_B200 * 8;
+  fp64_peak_kernel<<<grid, 256, 0, s>>>(g_peak_sink, iters);
+  RCC_CUDA(cudaGetLastError());
+  return (double)grid * 256.0 * (double)iters * 64.0;  // FMAs
+}
+
+}  // namespace rcc

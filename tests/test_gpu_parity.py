@@ -1,0 +1,153 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerance: 1e-9 relative (per-block Frobenius) in FP64 for residuals,
+Jacobians, normal equations and the reduced system -- BASELINE.json north_star.
+Converged parameters: 1e-6 rad / 1e-6 m.
+"""
+import numpy as np
+import pytest
+
+import ba_oracle as O
+from helpers import max_block_rel, oracle_blocks, oracle_reduced, rel_fro, to_oracle
+from robot_camera_calibration_b200.problem import BAProblem
+from robot_camera_calibration_b200.scenes import config_scene, make_scene
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+SCENES = {
+    "single": dict(n_markers=12, n_views=30, visibility=0.7, seed=11),
+    "single_2cam": dict(n_markers=14, n_views=24, visibility=0.7, n_cam=2, seed=12),
+    "rig": dict(n_markers=16, n_views=20, visibility=0.6, n_cam=3, model="rig", seed=13),
+}
+
+
+def _scene(name):
+    kw = dict(SCENES[name])
+    s = make_scene(kw.pop("n_markers"), kw.pop("n_views"), kw.pop("visibility"), **kw)
+    if name == "single_2cam":
+        # a "single" model with two cameras: every view belongs to one camera
+        cam_of_view = np.arange(len(s.views)) % 2
+        keep = s.cam_idx == cam_of_view[s.view_idx]
+        s.view_idx, s.marker_idx, s.cam_idx, s.pixels = (s.view_idx[keep], s.marker_idx[keep],
+                                                         s.cam_idx[keep], s.pixels[keep])
+    return s
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_evaluate_matches_oracle(name):
+    s = _scene(name)
+    p = to_oracle(s)
+    r = O.residuals(p)
+    Jb = O.jacobian_blocks_cs(p)
+    with BAProblem.from_scene(s) as gp:
+        out = gp.evaluate()
+    assert abs(out["cost"] - O.cost(p)) <= TOL * O.cost(p)
+    assert max_block_rel(out["residuals"], r) < TOL
+    for k in Jb:
+        assert max_block_rel(out["jacobians"][k], Jb[k]) < TOL, k
+
+
+@pytest.mark.parametrize("elim", ["views", "markers"])
+@pytest.mark.parametrize("name", list(SCENES))
+def test_normal_equations_match_oracle(name, elim):
+    s = _scene(name)
+    p = to_oracle(s)
+    ob = oracle_blocks(p, elim == "views")
+    with BAProblem.from_scene(s, eliminate=elim) as gp:
+        cost = gp.linearize()
+        nb = gp.normal_blocks()
+    assert abs(cost - ob["cost"]) <= TOL * ob["cost"]
+    scale_e = np.linalg.norm(ob["Hee"].reshape(len(ob["Hee"]), -1), axis=1).max()
+    for k in ("Hee", "Hff", "W", "ge", "gf", "Hes", "Hfs"):
+        floor = 1e-6 * np.abs(ob[k]).max()
+        assert max_block_rel(nb[k], ob[k], floor=floor) < TOL, (k, scale_e)
+    assert rel_fro(nb["Hss"], ob["Hss"]) < TOL
+    assert rel_fro(nb["gs"], ob["gs"]) < TOL
+
+
+@pytest.mark.parametrize("elim", ["views", "markers"])
+@pytest.mark.parametrize("name", list(SCENES))
+def test_schur_and_step_match_oracle(name, elim):
+    s = _scene(name)
+    p = to_oracle(s)
+    radius = 1e4
+    S, b, f_index, H, g, d2 = oracle_reduced(p, elim == "views", radius)
+    with BAProblem.from_scene(s, eliminate=elim) as gp:
+        gp.linearize()
+        gp.schur(radius)
+        Sg, bg = gp.reduced_system()
+        mcc, step_norm, x_norm = gp.solve_step()
+        st = gp.step()
+        c_new = gp.candidate_cost()
+    assert rel_fro(Sg, S) < TOL
+    assert rel_fro(bg, b) < TOL
+    delta, mcc_o, c, gmax = O.lm_step(p, radius)
+    o_view, o_marker, o_shared, n = p.offsets()
+    nv, nm = len(p.views), len(p.markers)
+    dv, dm, ds = delta[o_view:o_marker].reshape(nv, 6), delta[o_marker:o_shared].reshape(nm, 6), delta[o_shared:]
+    de, df = (dv, dm) if elim == "views" else (dm, dv)
+    # the step solves a system with condition number >> 1: compare at 1e-6 relative
+    assert rel_fro(st["d_e"], de) < 1e-6
+    assert rel_fro(st["d_f"], df) < 1e-6
+    assert rel_fro(st["d_shared"], ds) < 1e-6
+    assert abs(mcc - mcc_o) <= 1e-6 * abs(mcc_o)
+    assert abs(step_norm - np.linalg.norm(delta)) <= 1e-6 * np.linalg.norm(delta)
+    cand = p.copy()
+    cand.unpack(p.pack() + delta)
+    assert abs(c_new - O.cost(cand)) <= 1e-6 * O.cost(cand)
+
+
+@pytest.mark.parametrize("name,elim", [("single", "views"), ("single", "markers"), ("rig", "views")])
+def test_converged_parameters_match_oracle(name, elim):
+    s = _scene(name)
+    p = to_oracle(s)
+    O.lm_solve(p, max_iters=60)
+    with BAProblem.from_scene(s, eliminate=elim) as gp:
+        summ = gp.solve(max_iterations=60, function_tolerance=1e-15, gradient_tolerance=1e-12,
+                        parameter_tolerance=1e-14)
+        views, markers = gp.get_view_poses(), gp.get_marker_poses()
+        intr, dist = gp.get_intrinsics()
+        ext = gp.get_rig_extrinsics() if s.model == "rig" else None
+    assert summ["final_cost"] <= summ["initial_cost"]
+    assert abs(summ["final_cost"] - O.cost(p)) <= 1e-9 * O.cost(p)
+    # 1e-6 rad / 1e-6 m (BASELINE.json north_star)
+    assert np.abs(views - p.views).max() < 1e-6
+    assert np.abs(markers - p.markers).max() < 1e-6
+    assert np.abs(intr - p.intr).max() < 1e-4      # pixels
+    assert np.abs(dist - p.dist).max() < 1e-6
+    if ext is not None:
+        assert np.abs(ext - p.ext).max() < 1e-6
+
+
+def test_eval_failure_is_reported():
+    s = _scene("single")
+    from robot_camera_calibration_b200.scenes import compose
+    # turn camera 3 around its own y axis by pi: every tag it saw is now behind it
+    s.views[3] = compose(s.views[3], np.array([0.0, np.pi, 0.0, 0.0, 0.0, 0.0]))
+    assert (O.depths(to_oracle(s)) <= 0).any()
+    with BAProblem.from_scene(s) as gp:
+        out = gp.evaluate(allow_failure=True)
+    assert out["failed"]
+
+
+def test_cfg1_scene_full_size():
+    """BASELINE configs[0]: 20 tags x 200 views -- evaluate + linearise parity at full size."""
+    s = config_scene(1)
+    p = to_oracle(s)
+    r = O.residuals(p)
+    Jb = O.jacobian_blocks_cs(p)
+    with BAProblem.from_scene(s) as gp:
+        out = gp.evaluate()
+        cost = gp.linearize()
+        nb = gp.normal_blocks()
+    assert max_block_rel(out["residuals"], r) < TOL
+    for k in Jb:
+        assert max_block_rel(out["jacobians"][k], Jb[k]) < TOL
+    Je, Jf = Jb["view"], Jb["marker"]
+    W = np.einsum('nri,nrj->nij', Je, Jf)
+    assert max_block_rel(nb["W"], W, floor=1e-6 * np.abs(W).max()) < TOL
+    Hee = np.zeros((len(s.views), 6, 6))
+    np.add.at(Hee, s.view_idx, np.einsum('nri,nrj->nij', Je, Je))
+    assert max_block_rel(nb["Hee"], Hee) < TOL
+    assert abs(cost - O.cost(p)) <= TOL * O.cost(p)
