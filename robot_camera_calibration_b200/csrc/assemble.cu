@@ -26,16 +26,43 @@
 
 namespace rcc {
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#ifndef RCC_K2_MIN_CTAS
+#define RCC_K2_MIN_CTAS 3
+#endif
+
+// per-warp shared memory (doubles): staged rows | 2 x BPW other-pose records | own pose, ext pose, shared params
+template <bool RIG>
+struct WarpSmem {
+  using PG = PassGeom<RIG>;
+  static constexpr int ROWS = 0;
+  static constexpr int STAGE = PG::WARP_SMEM;
+  static constexpr int CONSTS = STAGE + 2 * PG::BPW * POSEX;
+  static constexpr int TOTAL = CONSTS + 2 * POSEX + 16;
+};
+
 template <bool RIG, bool EPASS, bool OWN_IS_VIEW>
-__global__ void __launch_bounds__(PassGeom<RIG>::WARPS * 32)
+__global__ void __launch_bounds__(PassGeom<RIG>::WARPS * 32, RCC_K2_MIN_CTAS)
 assemble_kernel(const AssembleArgs a) {
   using PG = PassGeom<RIG>;
-  constexpr int TPB = PG::TPB, BPW = PG::BPW, NCOL = PG::NCOL, BS = PG::BLK_STRIDE;
-  extern __shared__ double smem[];
+  using WS = WarpSmem<RIG>;
+  constexpr int TPB = PG::TPB, BPW = PG::BPW, NCOL = PG::RS, BS = PG::BLK_STRIDE, RSTR = PG::RED_STRIDE;
+  extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk_id = blockIdx.x * PG::WARPS + warp;
   if (chunk_id >= a.n_chunks) return;  // whole warp leaves together
-  double* rows = smem + warp * PG::WARP_SMEM;
+  double* wsm = smem + warp * WS::TOTAL;
+  double* rows = wsm + WS::ROWS;
+  double* stage = wsm + WS::STAGE;    // [2][BPW][POSEX] expanded pose of the other block, double buffered
+  double* own_x = wsm + WS::CONSTS;   // [POSEX] expanded pose of the own block
+  double* ext_x = own_x + POSEX;      // [POSEX] body_T_cam (rig)
+  double* sh = ext_x + POSEX;         // [SP] shared parameters of the chunk's camera
 
   const Chunk ch = a.chunks[chunk_id];
   const int b = lane / TPB;
@@ -44,28 +71,67 @@ assemble_kernel(const AssembleArgs a) {
   const bool lane_on = (lane < BPW * TPB) && (gi_id != G_NONE);
   const int gi = gi_id * 6, gj = gj_id * 6;
   const bool eval_lane = (lane < BPW * TPB) && (t < 4);
+  const double* oth_table = OWN_IS_VIEW ? a.marker_x : a.view_x;
+
+  // chunk constants -> shared memory
+  {
+    const double* src = (OWN_IS_VIEW ? a.view_x : a.marker_x) + (size_t)ch.own * POSEX;
+    if (lane < POSEX) own_x[lane] = src[lane];
+    if (RIG && lane < POSEX) ext_x[lane] = a.ext_x[(size_t)ch.cam * POSEX + lane];
+    if (lane < PG::SP) sh[lane] = a.shared[ch.cam * PG::SP + lane];
+  }
+  // software pipeline: other-block indices two iterations ahead (lane q holds block q),
+  // other-block pose records one iteration ahead (cp.async into stage[buf])
+  auto load_oth = [&](int it) -> int {
+    return (lane < BPW && it + lane < ch.count) ? a.oth[(int64_t)ch.start + it + lane] : 0;
+  };
+  auto issue_stage = [&](int it, int buf, int oth_reg) {
+    // BPW records x 12 16-byte pieces
+    constexpr int PIECES = BPW * (POSEX / 2);
+#pragma unroll
+    for (int r = 0; r < (PIECES + 31) / 32; ++r) {   // uniform trip count: the shuffle needs every lane
+      const int idx = lane + 32 * r;
+      const int q = min(idx / (POSEX / 2), BPW - 1), c = idx - q * (POSEX / 2);
+      const int o = __shfl_sync(0xffffffffu, oth_reg, q);
+      if (idx < PIECES && it + q < ch.count)
+        cp_async16(stage + (buf * BPW + q) * POSEX + 2 * c, oth_table + (size_t)o * POSEX + 2 * c);
+    }
+    cp_async_commit();
+  };
+  int oth_cur = load_oth(0);
+  int oth_nxt = load_oth(BPW);
+  issue_stage(0, 0, oth_cur);
+  double2 px_nxt = make_double2(0.0, 0.0);
+  if (eval_lane && b < ch.count) px_nxt = *reinterpret_cast<const double2*>(a.pix + ((int64_t)ch.start + b) * 8 + 2 * t);
 
   double acc[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-
-  const double* sh = a.shared + ch.cam * PG::SP;
-  const double* xx = RIG ? a.ext_x + ch.cam * POSEX : nullptr;
   double* blk = rows + b * BS;
+  int buf = 0;
 
-  for (int it = 0; it < ch.count; it += BPW) {
+  for (int it = 0; it < ch.count; it += BPW, buf ^= 1) {
     const bool valid = (it + b) < ch.count;
     const int64_t g = (int64_t)ch.start + it + b;
+    cp_async_wait_all();
+    __syncwarp();
+    // prefetch for the next iterations (overlaps with this iteration's arithmetic)
+    const double2 px = px_nxt;
+    if (it + BPW < ch.count) {
+      issue_stage(it + BPW, buf ^ 1, oth_nxt);
+      oth_nxt = load_oth(it + 2 * BPW);
+      if (eval_lane && it + BPW + b < ch.count)
+        px_nxt = *reinterpret_cast<const double2*>(a.pix + (g + BPW) * 8 + 2 * t);
+    }
     // ---- phase 1: corner evaluation ---------------------------------------
     if (valid && eval_lane) {
-      const int oth = a.oth[g];
-      const int vi = OWN_IS_VIEW ? ch.own : oth;
-      const int mi = OWN_IS_VIEW ? oth : ch.own;
+      const double* ox_rec = stage + (buf * BPW + b) * POSEX;
+      const double* vx = OWN_IS_VIEW ? own_x : ox_rec;
+      const double* mx = OWN_IS_VIEW ? ox_rec : own_x;
       BlockGeom<RIG> geo;
-      block_geometry<RIG>(a.view_x + (size_t)vi * POSEX, a.marker_x + (size_t)mi * POSEX, xx, geo);
+      block_geometry<RIG>(vx, mx, RIG ? ext_x : nullptr, geo);
       double ox, oy;
-      corner_xy(t, 0.5 * a.sizes[mi], ox, oy);
-      const double2 px = *reinterpret_cast<const double2*>(a.pix + g * 8 + 2 * t);
+      corner_xy(t, mx[PX_HS], ox, oy);
       CornerRows<RIG> c;
       eval_corner<RIG, true>(geo, sh, ox, oy, px.x, px.y, c);
       if (!(c.depth > 0.0) || !isfinite(c.r[0]) || !isfinite(c.r[1])) *a.fail_flag = 1;
@@ -125,14 +191,14 @@ assemble_kernel(const AssembleArgs a) {
 
   // ---- chunk epilogue: sum the BPW thread-groups, one partial per tile ------
 #pragma unroll
-  for (int k = 0; k < 36; ++k) rows[k * 32 + lane] = acc[k];
+  for (int k = 0; k < 36; ++k) rows[lane * RSTR + k] = acc[k];
   __syncwarp();
   double* out = a.partials + (size_t)chunk_id * (TPB * 36);
   for (int o = lane; o < TPB * 36; o += 32) {
     const int tt = o / 36, k = o - tt * 36;
     double s = 0.0;
 #pragma unroll
-    for (int bb = 0; bb < BPW; ++bb) s += rows[k * 32 + bb * TPB + tt];
+    for (int bb = 0; bb < BPW; ++bb) s += rows[(bb * TPB + tt) * RSTR + k];
     out[o] = s;
   }
 }
@@ -141,7 +207,7 @@ template <bool RIG, bool EPASS, bool OWN_IS_VIEW>
 static void launch_assemble_t(const AssembleArgs& a, cudaStream_t s) {
   using PG = PassGeom<RIG>;
   if (a.n_chunks == 0) return;
-  const size_t smem = PG::WARPS * PG::WARP_SMEM * sizeof(double);
+  const size_t smem = PG::WARPS * WarpSmem<RIG>::TOTAL * sizeof(double);
   auto k = assemble_kernel<RIG, EPASS, OWN_IS_VIEW>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -223,102 +289,120 @@ void launch_finalize_side(bool rig, bool epass, const FinalizeSideArgs& a, cudaS
   RCC_CUDA(cudaGetLastError());
 }
 
-// CTA-wide fixed-order reduction of one tile over a chunk list -> out36 (smem)
-__device__ void reduce_tile(const double* __restrict__ partials, int tpb, int tile, const int32_t* __restrict__ list,
-                            int n_list, double* red /*[7*36]*/, double* out36) {
-  const int tid = threadIdx.x;
-  const int slice = tid / 36, k = tid - 36 * slice;
-  if (slice < 7) {
-    double s = 0.0;
-    for (int q = slice; q < n_list; q += 7) s += partials[(size_t)list[q] * (tpb * 36) + tile * 36 + k];
-    red[slice * 36 + k] = s;
+// ---------------------------------------------------------------------------
+// finalize_shared: shared x shared tiles, gradient and cost per camera.
+// Stage 1: CTA (slice, camera) sums its share of the camera's chunk list for
+// every shared tile (fixed order).  Stage 2: one CTA per camera sums the
+// FIN_SLICES partials in order and scatters them into H_ss / g_s / cost.
+// ---------------------------------------------------------------------------
+struct SharedTile { int from_f; int tile; };
+template <bool RIG>
+__device__ __forceinline__ SharedTile shared_tile(int q) {
+  // q: 0 S1S1 (E)  1 S1S2 (F)  2 S2S2 (F)  3 S1X (E)  4 XX (E)  5 S2X (F)
+  switch (q) {
+    case 0: return {0, RIG ? 5 : 4};
+    case 1: return {1, RIG ? 4 : 3};
+    case 2: return {1, RIG ? 5 : 4};
+    case 3: return {0, 6};
+    case 4: return {0, 7};
+    default: return {1, 6};
   }
-  __syncthreads();
-  if (tid < 36) {
-    double s = 0.0;
-#pragma unroll
-    for (int q = 0; q < 7; ++q) s += red[q * 36 + tid];
-    out36[tid] = s;
-  }
-  __syncthreads();
 }
 
 template <bool RIG>
-__global__ void __launch_bounds__(256) finalize_shared_kernel(const FinalizeSharedArgs a) {
-  using PG = PassGeom<RIG>;
-  constexpr int TPB = PG::TPB, SP = PG::SP;
+__global__ void __launch_bounds__(256) finalize_shared_partial_kernel(const FinalizeSharedArgs a) {
+  constexpr int TPB = PassGeom<RIG>::TPB, NQ = RIG ? 6 : 3;
   __shared__ double red[7 * 36];
-  __shared__ double tile[36];
+  const int slice = blockIdx.x, cam = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int sl = tid / 36, k = tid - 36 * sl;
+  for (int q = 0; q < NQ; ++q) {
+    const SharedTile st = shared_tile<RIG>(q);
+    const double* part = st.from_f ? a.part_f : a.part_e;
+    const int32_t* list = st.from_f ? a.cam_chunks_f + a.cam_ptr_f[cam] : a.cam_chunks_e + a.cam_ptr_e[cam];
+    const int n = st.from_f ? a.cam_ptr_f[cam + 1] - a.cam_ptr_f[cam] : a.cam_ptr_e[cam + 1] - a.cam_ptr_e[cam];
+    const int per = (n + FIN_SLICES - 1) / FIN_SLICES;
+    const int lo = slice * per, hi = min(n, lo + per);
+    if (sl < 7) {
+      double s = 0.0;
+      for (int c = lo + sl; c < hi; c += 7) s += part[(size_t)list[c] * (TPB * 36) + st.tile * 36 + k];
+      red[sl * 36 + k] = s;
+    }
+    __syncthreads();
+    if (tid < 36) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 7; ++w) s += red[w * 36 + tid];
+      a.scratch[(((size_t)cam * FIN_SLICES + slice) * 6 + q) * 36 + tid] = s;
+    }
+    __syncthreads();
+  }
+}
+
+template <bool RIG>
+__global__ void __launch_bounds__(256) finalize_shared_final_kernel(const FinalizeSharedArgs a) {
+  constexpr int SP = PassGeom<RIG>::SP, NQ = RIG ? 6 : 3;
+  __shared__ double tile[6][36];
   const int cam = blockIdx.x;
   const int tid = threadIdx.x;
   const int ns = a.n_shared;
   double* H = a.Hss;
   const int base = cam * SP;
   for (int k = tid; k < SP * ns; k += blockDim.x) H[(size_t)base * ns + k] = 0.0;
-  __syncthreads();
-  const int32_t* le = a.cam_chunks_e + a.cam_ptr_e[cam];
-  const int ne = a.cam_ptr_e[cam + 1] - a.cam_ptr_e[cam];
-  const int32_t* lf = a.cam_chunks_f + a.cam_ptr_f[cam];
-  const int nf = a.cam_ptr_f[cam + 1] - a.cam_ptr_f[cam];
-  const int r = tid / 6, q = tid - 6 * r;  // valid for tid < 36
-
-  // S1 x S1  (E pass)
-  reduce_tile(a.part_e, TPB, RIG ? 5 : 4, le, ne, red, tile);
-  if (tid < 36) H[(size_t)(base + r) * ns + base + q] = tile[tid];
-  __syncthreads();
-  // S1 x S2  (F pass): cols 0..2 -> p1 p2 k3, col 3 -> gradient of S1
-  reduce_tile(a.part_f, TPB, RIG ? 4 : 3, lf, nf, red, tile);
-  if (tid < 36) {
-    if (q < 3) {
-      H[(size_t)(base + r) * ns + base + 6 + q] = tile[tid];
-      H[(size_t)(base + 6 + q) * ns + base + r] = tile[tid];
-    } else if (q == 3) {
-      a.gs[base + r] = tile[tid];
-    }
+  if (tid < NQ * 36) {
+    const int q = tid / 36, k = tid - 36 * q;
+    double s = 0.0;
+    for (int sl = 0; sl < FIN_SLICES; ++sl) s += a.scratch[(((size_t)cam * FIN_SLICES + sl) * 6 + q) * 36 + k];
+    tile[q][k] = s;
   }
   __syncthreads();
-  // S2 x S2  (F pass)
-  reduce_tile(a.part_f, TPB, RIG ? 5 : 4, lf, nf, red, tile);
-  if (tid < 36) {
-    if (r < 3 && q < 3) H[(size_t)(base + 6 + r) * ns + base + 6 + q] = tile[tid];
-    else if (r < 3 && q == 3) a.gs[base + 6 + r] = tile[tid];
-    else if (r == 3 && q == 3) a.cost2_cam[cam] = tile[tid];
+  if (tid >= 36) return;
+  const int r = tid / 6, q = tid - 6 * r;
+  // S1 x S1
+  H[(size_t)(base + r) * ns + base + q] = tile[0][tid];
+  // S1 x S2: cols 0..2 -> p1 p2 k3, col 3 -> gradient of S1
+  if (q < 3) {
+    H[(size_t)(base + r) * ns + base + 6 + q] = tile[1][tid];
+    H[(size_t)(base + 6 + q) * ns + base + r] = tile[1][tid];
+  } else if (q == 3) {
+    a.gs[base + r] = tile[1][tid];
   }
-  __syncthreads();
+  // S2 x S2
+  if (r < 3 && q < 3) H[(size_t)(base + 6 + r) * ns + base + 6 + q] = tile[2][tid];
+  else if (r < 3 && q == 3) a.gs[base + 6 + r] = tile[2][tid];
+  else if (r == 3 && q == 3) a.cost2_cam[cam] = tile[2][tid];
   if (RIG) {
-    // S1 x X (E pass)
-    reduce_tile(a.part_e, TPB, 6, le, ne, red, tile);
-    if (tid < 36) {
-      H[(size_t)(base + r) * ns + base + 9 + q] = tile[tid];
-      H[(size_t)(base + 9 + q) * ns + base + r] = tile[tid];
-    }
-    __syncthreads();
-    // X x X (E pass)
-    reduce_tile(a.part_e, TPB, 7, le, ne, red, tile);
-    if (tid < 36) H[(size_t)(base + 9 + r) * ns + base + 9 + q] = tile[tid];
-    __syncthreads();
-    // S2 x X (F pass): rows 0..2 -> p1 p2 k3, row 3 -> gradient of X
-    reduce_tile(a.part_f, TPB, 6, lf, nf, red, tile);
-    if (tid < 36) {
-      if (r < 3) {
-        H[(size_t)(base + 6 + r) * ns + base + 9 + q] = tile[tid];
-        H[(size_t)(base + 9 + q) * ns + base + 6 + r] = tile[tid];
-      } else if (r == 3) {
-        a.gs[base + 9 + q] = tile[tid];
-      }
+    // S1 x X
+    H[(size_t)(base + r) * ns + base + 9 + q] = tile[3][tid];
+    H[(size_t)(base + 9 + q) * ns + base + r] = tile[3][tid];
+    // X x X
+    H[(size_t)(base + 9 + r) * ns + base + 9 + q] = tile[4][tid];
+    // S2 x X: rows 0..2 -> p1 p2 k3, row 3 -> gradient of X
+    if (r < 3) {
+      H[(size_t)(base + 6 + r) * ns + base + 9 + q] = tile[5][tid];
+      H[(size_t)(base + 9 + q) * ns + base + 6 + r] = tile[5][tid];
+    } else if (r == 3) {
+      a.gs[base + 9 + q] = tile[5][tid];
     }
   }
 }
 
 void launch_finalize_shared(bool rig, const FinalizeSharedArgs& a, cudaStream_t s) {
-  if (rig) finalize_shared_kernel<true><<<a.n_cam, 256, 0, s>>>(a);
-  else finalize_shared_kernel<false><<<a.n_cam, 256, 0, s>>>(a);
+  dim3 grid(FIN_SLICES, a.n_cam);
+  if (rig) {
+    finalize_shared_partial_kernel<true><<<grid, 256, 0, s>>>(a);
+    finalize_shared_final_kernel<true><<<a.n_cam, 256, 0, s>>>(a);
+  } else {
+    finalize_shared_partial_kernel<false><<<grid, 256, 0, s>>>(a);
+    finalize_shared_final_kernel<false><<<a.n_cam, 256, 0, s>>>(a);
+  }
   RCC_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
 __global__ void expand_poses_kernel(const double* __restrict__ views, int n_views, double* __restrict__ view_x,
-                                    const double* __restrict__ markers, int n_markers, double* __restrict__ marker_x,
+                                    const double* __restrict__ markers, const double* __restrict__ sizes,
+                                    int n_markers, double* __restrict__ marker_x,
                                     const double* __restrict__ shared, int n_cam, int sp, double* __restrict__ ext_x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_views) {
@@ -326,16 +410,18 @@ __global__ void expand_poses_kernel(const double* __restrict__ views, int n_view
   } else if (i < n_views + n_markers) {
     const int j = i - n_views;
     expand_pose(markers + (size_t)j * 6, marker_x + (size_t)j * POSEX);
+    marker_x[(size_t)j * POSEX + PX_HS] = 0.5 * sizes[j];  // half tag size rides in the record's padding
   } else if (i < n_views + n_markers + n_cam && sp == 15) {
     const int j = i - n_views - n_markers;
     expand_pose(shared + (size_t)j * sp + 9, ext_x + (size_t)j * POSEX);
   }
 }
 
-void launch_expand_poses(const double* views, int n_views, double* view_x, const double* markers, int n_markers,
-                         double* marker_x, const double* shared, int n_cam, int sp, double* ext_x, cudaStream_t s) {
+void launch_expand_poses(const double* views, int n_views, double* view_x, const double* markers,
+                         const double* sizes, int n_markers, double* marker_x, const double* shared, int n_cam, int sp,
+                         double* ext_x, cudaStream_t s) {
   const int n = n_views + n_markers + n_cam;
-  expand_poses_kernel<<<ceil_div(n, 128), 128, 0, s>>>(views, n_views, view_x, markers, n_markers, marker_x, shared,
+  expand_poses_kernel<<<ceil_div(n, 128), 128, 0, s>>>(views, n_views, view_x, markers, sizes, n_markers, marker_x, shared,
                                                        n_cam, sp, ext_x);
   RCC_CUDA(cudaGetLastError());
 }

@@ -26,9 +26,13 @@ template <bool RIG>
 struct PassGeom {
   static constexpr int TPB = RIG ? 8 : 5;     // tiles (= lanes) per observation block
   static constexpr int BPW = RIG ? 4 : 6;     // observation blocks per warp iteration
-  static constexpr int NCOL = RIG ? 30 : 24;  // doubles per staged row
-  static constexpr int BLK_STRIDE = 8 * NCOL + 2;  // +2 doubles: de-phase the blocks across banks
-  static constexpr int WARP_SMEM = (BPW * BLK_STRIDE > 36 * 32) ? BPW * BLK_STRIDE : 36 * 32;  // doubles
+  static constexpr int NCOL = RIG ? 30 : 24;  // doubles used per staged row
+  // Row stride in doubles: RS/2 odd so the 4 corner lanes of a block (rows 2t) land in 4 different
+  // 16-byte bank groups; block stride/2 == 1 (mod 8) so the blocks of a warp iteration tile the rest.
+  static constexpr int RS = RIG ? 30 : 26;
+  static constexpr int BLK_STRIDE = 8 * RS + 2;
+  static constexpr int RED_STRIDE = 37;        // epilogue: lane-major, odd stride
+  static constexpr int WARP_SMEM = (BPW * BLK_STRIDE > RED_STRIDE * 32) ? BPW * BLK_STRIDE : RED_STRIDE * 32;  // doubles
   static constexpr int SP = RIG ? 15 : 9;     // shared parameters per camera
   static constexpr int WARPS = 4;             // warps (= chunks) per CTA
 };
@@ -109,12 +113,15 @@ struct FinalizeSharedArgs {
   double* Hss;                  // [n_shared*n_shared] block diagonal (zeroed by the kernel)
   double* gs;                   // [n_shared]
   double* cost2_cam;            // [n_cam] sum r^2 per camera
+  double* scratch;              // [n_cam * FIN_SLICES * 6 * 36] first-stage partial tiles
 };
+constexpr int FIN_SLICES = 64;  // CTAs per camera in the first stage of finalize_shared
 void launch_finalize_shared(bool rig, const FinalizeSharedArgs& a, cudaStream_t s);
 
 // pose expansion: rvec,t -> R, Jr, t
-void launch_expand_poses(const double* views, int n_views, double* view_x, const double* markers, int n_markers,
-                         double* marker_x, const double* shared, int n_cam, int sp, double* ext_x, cudaStream_t s);
+void launch_expand_poses(const double* views, int n_views, double* view_x, const double* markers,
+                         const double* sizes, int n_markers, double* marker_x, const double* shared, int n_cam, int sp,
+                         double* ext_x, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // K1 / K6: materialised evaluation and cost-only evaluation

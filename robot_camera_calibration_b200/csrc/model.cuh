@@ -26,6 +26,7 @@ namespace rcc {
 // stored as 24 doubles (21 used) so one pose is 6 x 32-byte sectors.
 constexpr int POSEX = 24;
 constexpr int PX_R = 0, PX_JR = 9, PX_T = 18;
+constexpr int PX_HS = 21;  // marker records: half tag size (filled by expand_poses_kernel)
 
 // sin(t)/t, accurate for all t >= 0
 RCC_HD double sinc_d(double t2, double t) {

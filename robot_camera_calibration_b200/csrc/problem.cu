@@ -354,7 +354,7 @@ static void refresh_constants(P_t* P) {
 static void ensure_expanded(P_t* P) {
   if (P->expanded_valid) return;
   Scoped t(P, ST_EXPAND, 1);
-  launch_expand_poses(P->views.p, P->n_views, P->view_x.p, P->markers.p, P->n_markers, P->marker_x.p, P->shared.p,
+  launch_expand_poses(P->views.p, P->n_views, P->view_x.p, P->markers.p, P->sizes.p, P->n_markers, P->marker_x.p, P->shared.p,
                       P->n_cam, P->sp, P->ext_x.p, P->stream);
   P->expanded_valid = true;
 }
@@ -391,13 +391,13 @@ static void do_linearize(P_t* P) {
     launch_assemble(P->rig, false, !P->elim_view, a, P->stream);
   }
   {
-    Scoped t(P, ST_FINALIZE, 3);
+    Scoped t(P, ST_FINALIZE, 4);
     FinalizeSideArgs fe{P->part_e.p, P->e_chunks.p, P->e_chunk_ptr.p, P->n_e, P->n_shared, P->Hee.p, P->ge.p, P->Hes.p};
     launch_finalize_side(P->rig, true, fe, P->stream);
     FinalizeSideArgs ff{P->part_f.p, P->f_chunks.p, P->f_chunk_ptr.p, P->n_f, P->n_shared, P->Hff.p, P->gf.p, P->Hfs.p};
     launch_finalize_side(P->rig, false, ff, P->stream);
     FinalizeSharedArgs fs{P->part_e.p, P->part_f.p, P->cam_chunks_e.p, P->cam_ptr_e.p, P->cam_chunks_f.p,
-                          P->cam_ptr_f.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p};
+                          P->cam_ptr_f.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p, P->fin_scratch.p};
     launch_finalize_shared(P->rig, fs, P->stream);
   }
   P->linearized = true;
@@ -542,7 +542,7 @@ static void do_candidate_cost(P_t* P) {
   RCC_REQUIRE(P->step_ready, RCC_NOT_READY, "solve_step has not been called");
   {
     Scoped t(P, ST_EXPAND, 1);
-    launch_expand_poses(P->views_c.p, P->n_views, P->view_xc.p, P->markers_c.p, P->n_markers, P->marker_xc.p,
+    launch_expand_poses(P->views_c.p, P->n_views, P->view_xc.p, P->markers_c.p, P->sizes.p, P->n_markers, P->marker_xc.p,
                         P->shared_c.p, P->n_cam, P->sp, P->ext_xc.p, P->stream);
   }
   {
@@ -776,6 +776,7 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     P->c_intr.assign(P->n_cam, 0); P->c_dist.assign(P->n_cam, 0); P->c_ext.assign(P->n_cam, 0);
     P->Hee.alloc((size_t)P->n_e * 36); P->ge.alloc((size_t)P->n_e * 6); P->Hes.alloc((size_t)P->n_e * 6 * P->n_shared);
     P->Hff.alloc((size_t)P->n_f * 36); P->gf.alloc((size_t)P->n_f * 6); P->Hfs.alloc((size_t)P->n_f * 6 * P->n_shared);
+    P->fin_scratch.alloc((size_t)P->n_cam * FIN_SLICES * 6 * 36);
     P->Hss.alloc((size_t)P->n_shared * P->n_shared); P->gs.alloc((size_t)P->n_shared); P->cost2_cam.alloc(P->n_cam);
     P->Linv.alloc((size_t)P->n_e * 36); P->Yb.alloc((size_t)P->n_e * P->n_bb * 36); P->d2e.alloc((size_t)P->n_e * 6);
     P->S.alloc((size_t)(P->n_red + 3) * P->ld); P->S.zero(s);

@@ -67,7 +67,7 @@ struct rcc_ba_problem {
   rcc::DBuf<uint8_t> e_const;
 
   // linearisation products
-  rcc::DBuf<double> part_e, part_f, W, Hee, ge, Hes, Hff, gf, Hfs, Hss, gs, cost2_cam;
+  rcc::DBuf<double> fin_scratch, part_e, part_f, W, Hee, ge, Hes, Hff, gf, Hfs, Hss, gs, cost2_cam;
   // Schur / step
   rcc::DBuf<double> Linv, Y, Yb, d2e, S, shared_scratch, rhs, d2f, gFm, delta_F, delta_e, bs_partials, stats;
   rcc::DBuf<int32_t> const_idx, fail_flag;

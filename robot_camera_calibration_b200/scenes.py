@@ -160,12 +160,15 @@ def _look_at(cam_pos, target, roll):
 def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
                tag_size=0.1, pixel_noise=0.3, image_size=(640, 480),
                perturb=(0.02, 0.02, 0.01), round_pixels=False, chunk_views=256,
-               name="", dtype_idx=np.int32):
+               name="", dtype_idx=np.int32, view_seed=None):
     """Generate a synthetic marker scene.
 
     visibility : target fraction of tags seen per view (per camera); the wall
                  is sized so that the image footprint covers about that share.
     perturb    : (rad, m, relative-intrinsics) sigma of the initial guess.
+    view_seed  : if given, views / observations / noise come from a second
+                 generator seeded (seed, view_seed) while cameras and tags only
+                 depend on `seed` -- weak-scaling shards share one tag cloud.
     round_pixels: truncate pixels to int like corner_detections.cpp:53-54.
     """
     rng = np.random.default_rng(seed)
@@ -211,6 +214,12 @@ def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
     markers_t[0] = 0.0
     sizes = np.full(n_markers, tag_size)
 
+    if view_seed is not None:
+        # initial guesses of the shared blocks must not depend on the shard either
+        rng_shared = np.random.default_rng([seed, 7919])
+        rng = np.random.default_rng([seed, int(view_seed)])
+    else:
+        rng_shared = None
     # ---- views: look at a random point of the wall from d in [0.7,1.3] d_mean
     # (tags face -z of the wall frame towards the cameras: wall normal is +z,
     #  camera sits at negative z looking towards +z)
@@ -268,15 +277,16 @@ def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
     s_r, s_t, s_i = perturb
     views0 = views_t + np.concatenate([rng.normal(0, s_r, (n_views, 3)),
                                        rng.normal(0, s_t, (n_views, 3))], -1)
-    markers0 = markers_t + np.concatenate([rng.normal(0, s_r, (n_markers, 3)),
-                                           rng.normal(0, s_t, (n_markers, 3))], -1)
+    rs = rng if rng_shared is None else rng_shared
+    markers0 = markers_t + np.concatenate([rs.normal(0, s_r, (n_markers, 3)),
+                                           rs.normal(0, s_t, (n_markers, 3))], -1)
     markers0[0] = 0.0
-    intr0 = intr_t * (1 + rng.normal(0, s_i, intr_t.shape))
-    dist0 = dist_t + rng.normal(0, s_i, dist_t.shape) * 0.1
+    intr0 = intr_t * (1 + rs.normal(0, s_i, intr_t.shape))
+    dist0 = dist_t + rs.normal(0, s_i, dist_t.shape) * 0.1
     ext0 = ext_t.copy()
     if model == "rig" and n_cam > 1:
-        ext0[1:] += np.concatenate([rng.normal(0, s_r, (n_cam - 1, 3)),
-                                    rng.normal(0, s_t, (n_cam - 1, 3))], -1)
+        ext0[1:] += np.concatenate([rs.normal(0, s_r, (n_cam - 1, 3)),
+                                    rs.normal(0, s_t, (n_cam - 1, 3))], -1)
     return Scene(model=model, intr=intr0, dist=dist0, ext=ext0, views=views0,
                  markers=markers0, sizes=sizes, view_idx=view_idx, marker_idx=marker_idx,
                  cam_idx=cam_idx, pixels=pixels,

@@ -77,3 +77,19 @@ def oracle_reduced(p, elim_view, radius, min_diag=1e-6, max_diag=1e32):
     f_index = np.concatenate([np.arange(f_off, f_off + 6 * n_f), np.arange(o_shared, n)])
     S, b = O.schur_reduce(Hd, gd, slice(e_off, e_off + 6 * n_e), f_index)
     return S, b, f_index, H, g, d2
+
+
+def load_golden(name):
+    """tests/golden/<name>.npz -> (Scene, dict of expected arrays)."""
+    import os
+    from robot_camera_calibration_b200.scenes import Scene
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")))
+    s = Scene(model=str(g["model"]), intr=g["intr"], dist=g["dist"], ext=g["ext"], views=g["views"],
+              markers=g["markers"], sizes=g["sizes"], view_idx=g["view_idx"], marker_idx=g["marker_idx"],
+              cam_idx=g["cam_idx"], pixels=g["pixels"], const_views=g["const_views"],
+              const_markers=g["const_markers"], const_intr=g["const_intr"], const_dist=g["const_dist"],
+              const_ext=g["const_ext"])
+    return s, g
+
+
+GOLDEN = ("single_small", "rig_small", "single_intpix")

@@ -151,3 +151,31 @@ def test_cfg1_scene_full_size():
     np.add.at(Hee, s.view_idx, np.einsum('nri,nrj->nij', Je, Je))
     assert max_block_rel(nb["Hee"], Hee) < TOL
     assert abs(cost - O.cost(p)) <= TOL * O.cost(p)
+
+
+from helpers import GOLDEN, load_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_gpu_matches_committed_golden_vectors(name):
+    """CUDA path vs tests/golden/*.npz (OpenCV analytic derivatives for the
+    residuals / Jacobians, dense numpy for normal equations, Schur and step)."""
+    s, g = load_golden(name)
+    for elim in ("views", "markers"):
+        with BAProblem.from_scene(s, eliminate=elim) as gp:
+            out = gp.evaluate()
+            assert np.abs(out["residuals"] - g["residuals"]).max() < 1e-9
+            for k, J in out["jacobians"].items():
+                assert max_block_rel(J, g[f"jac_{k}"]) < TOL, k
+            cost = gp.linearize()
+            assert abs(cost - float(g["cost"])) <= TOL * float(g["cost"])
+            nb = gp.normal_blocks()
+            for k in ("Hee", "ge", "Hes", "Hff", "gf", "Hfs", "Hss", "gs", "W"):
+                assert rel_fro(nb[k], g[f"{elim}_{k}"]) < TOL, (elim, k)
+            gp.schur(float(g["radius"]))
+            S, b = gp.reduced_system()
+            assert rel_fro(S, g[f"{elim}_S"]) < TOL
+            assert rel_fro(b, g[f"{elim}_b"]) < TOL
+            mcc, step_norm, _ = gp.solve_step()
+            assert abs(step_norm - np.linalg.norm(g["delta"])) <= 1e-6 * np.linalg.norm(g["delta"])
+            assert abs(mcc - float(g["mcc"])) <= 1e-6 * abs(float(g["mcc"]))
