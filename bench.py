@@ -166,7 +166,7 @@ def run_reference(args):
                             "sample": f"first {args.ref_views} views ({obs} observations) per step; Ceres-equivalent "
                                       "C++/OpenMP restatement (Ceres and the reference optimiser do not exist here)"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    _emit(out)
 
 
 def run_ours(args):
@@ -341,13 +341,26 @@ def run_ours(args):
                         "reduced_system_n": int(d.n_reduced), "n_pairs": int(d.n_pairs)},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[0] > 0},
         }
-        print(json.dumps(out))
+        _emit(out)
     gp.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(obj):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any
+    library prints (NCCL banners, warnings) was re-routed to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the rest of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librcc_ba.so")
+LIB_PATH = os.environ.get("RCC_BA_LIB") or os.path.join(HERE, "librcc_ba.so")   # override: kernel-variant experiments
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

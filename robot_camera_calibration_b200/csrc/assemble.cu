@@ -26,6 +26,29 @@
 
 namespace rcc {
 
+// stores the column groups of one corner's two residual rows into the staged row layout
+// [O(6) | T(6) | S1(6) | S2: p1 p2 k3 r 0 0 | X(6)]
+template <bool RIG, bool OWN_IS_VIEW>
+struct RowSink {
+  double* row[2];
+  __device__ __forceinline__ void put6(int i, int col, const double* v) {
+    double2* d = reinterpret_cast<double2*>(row[i] + col);
+    d[0] = make_double2(v[0], v[1]);
+    d[1] = make_double2(v[2], v[3]);
+    d[2] = make_double2(v[4], v[5]);
+  }
+  __device__ __forceinline__ void shared(int i, const double* js, double r) {
+    put6(i, 12, js);
+    double2* d = reinterpret_cast<double2*>(row[i] + 18);
+    d[0] = make_double2(js[6], js[7]);
+    d[1] = make_double2(js[8], r);
+    d[2] = make_double2(0.0, 0.0);
+  }
+  __device__ __forceinline__ void marker(int i, const double* jm) { put6(i, OWN_IS_VIEW ? 6 : 0, jm); }
+  __device__ __forceinline__ void view(int i, const double* jv) { put6(i, OWN_IS_VIEW ? 0 : 6, jv); }
+  __device__ __forceinline__ void ext(int i, const double* jx) { put6(i, 24, jx); }
+};
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -34,7 +57,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 #ifndef RCC_K2_MIN_CTAS
-#define RCC_K2_MIN_CTAS 3
+#define RCC_K2_MIN_CTAS 2
 #endif
 
 // per-warp shared memory (doubles): staged rows | 2 x BPW other-pose records | own pose, ext pose, shared params
@@ -132,32 +155,10 @@ assemble_kernel(const AssembleArgs a) {
       block_geometry<RIG>(vx, mx, RIG ? ext_x : nullptr, geo);
       double ox, oy;
       corner_xy(t, mx[PX_HS], ox, oy);
-      CornerRows<RIG> c;
-      eval_corner<RIG, true>(geo, sh, ox, oy, px.x, px.y, c);
-      if (!(c.depth > 0.0) || !isfinite(c.r[0]) || !isfinite(c.r[1])) *a.fail_flag = 1;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        double2* row = reinterpret_cast<double2*>(blk + (2 * t + i) * NCOL);
-        const double* jo = OWN_IS_VIEW ? c.jv[i] : c.jm[i];
-        const double* jt = OWN_IS_VIEW ? c.jm[i] : c.jv[i];
-        row[0] = make_double2(jo[0], jo[1]);
-        row[1] = make_double2(jo[2], jo[3]);
-        row[2] = make_double2(jo[4], jo[5]);
-        row[3] = make_double2(jt[0], jt[1]);
-        row[4] = make_double2(jt[2], jt[3]);
-        row[5] = make_double2(jt[4], jt[5]);
-        row[6] = make_double2(c.js[i][0], c.js[i][1]);
-        row[7] = make_double2(c.js[i][2], c.js[i][3]);
-        row[8] = make_double2(c.js[i][4], c.js[i][5]);
-        row[9] = make_double2(c.js[i][6], c.js[i][7]);
-        row[10] = make_double2(c.js[i][8], c.r[i]);
-        row[11] = make_double2(0.0, 0.0);
-        if (RIG) {
-          row[12] = make_double2(c.jx[i][0], c.jx[i][1]);
-          row[13] = make_double2(c.jx[i][2], c.jx[i][3]);
-          row[14] = make_double2(c.jx[i][4], c.jx[i][5]);
-        }
-      }
+      RowSink<RIG, OWN_IS_VIEW> sink{blk + (2 * t) * NCOL, blk + (2 * t + 1) * NCOL};
+      double r0, r1;
+      const double depth = eval_corner_emit<RIG>(geo, sh, ox, oy, px.x, px.y, sink, r0, r1);
+      if (!(depth > 0.0) || !isfinite(r0) || !isfinite(r1)) *a.fail_flag = 1;
     }
     __syncwarp();
     // ---- phase 2: 6x6 tile  I^T J  over the block's 8 rows ----------------
@@ -237,54 +238,55 @@ void launch_assemble(bool rig, bool epass, bool own_is_view, const AssembleArgs&
 // finalize: one warp per own block sums its chunk partials in chunk order.
 // ---------------------------------------------------------------------------
 template <bool RIG, bool EPASS>
-__global__ void __launch_bounds__(128) finalize_side_kernel(const FinalizeSideArgs a) {
+__global__ void __launch_bounds__(160) finalize_side_kernel(const FinalizeSideArgs a) {
+  // one CTA per own block; thread (q, k) sums entry k of tile q over the block's chunks.
+  // q: 0 = O x O, 1 = O x S1, 2 = O x S2 (col 3 = gradient), 3 = O x X (rig)
   using PG = PassGeom<RIG>;
-  constexpr int TPB = PG::TPB, SP = PG::SP;
-  constexpr int T_S1 = EPASS ? 2 : 1, T_S2 = T_S1 + 1, T_X = T_S1 + 2;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (i >= a.n_own) return;
+  constexpr int TPB = PG::TPB, SP = PG::SP, NQ = RIG ? 4 : 3;
+  constexpr int T_S1 = EPASS ? 2 : 1;
+  const int i = blockIdx.x;
+  const int tid = threadIdx.x;
   double* hos = a.Hos + (size_t)i * 6 * a.n_shared;
-  for (int k = lane; k < 6 * a.n_shared; k += 32) hos[k] = 0.0;
-  __syncwarp();
-  double oo[2] = {0.0, 0.0}, gacc[2] = {0.0, 0.0};
-  for (int c = a.chunk_ptr[i]; c < a.chunk_ptr[i + 1]; ++c) {
-    const double* P = a.partials + (size_t)c * (TPB * 36);
-    const int cam = a.chunks[c].cam;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k = lane + 32 * h;
-      if (k < 36) {
-        const int r = k / 6, col = k - 6 * r;
-        oo[h] += P[k];
-        double* hrow = hos + r * a.n_shared + cam * SP;
-        hrow[col] += P[T_S1 * 36 + k];
-        if (col < 3) hrow[6 + col] += P[T_S2 * 36 + k];
-        else if (col == 3) gacc[h] += P[T_S2 * 36 + k];
-        if (RIG) hrow[9 + col] += P[T_X * 36 + k];
-      }
+  for (int k = tid; k < 6 * a.n_shared; k += blockDim.x) hos[k] = 0.0;
+  __syncthreads();
+  const int q = tid / 36, k = tid - 36 * q;
+  if (q >= NQ) return;
+  const int tile = (q == 0) ? 0 : T_S1 + (q - 1);
+  const int r = k / 6, col = k - 6 * r;
+  const int c0 = a.chunk_ptr[i], c1 = a.chunk_ptr[i + 1];
+  double total = 0.0, per_cam = 0.0;
+  int cam = (c0 < c1) ? a.chunks[c0].cam : 0;
+  auto flush = [&](int cm) {
+    double* hrow = hos + r * a.n_shared + cm * SP;
+    if (q == 1) hrow[col] = per_cam;
+    else if (q == 2 && col < 3) hrow[6 + col] = per_cam;
+    else if (q == 3) hrow[9 + col] = per_cam;
+    per_cam = 0.0;
+  };
+  for (int c = c0; c < c1; ++c) {
+    const int cm = a.chunks[c].cam;
+    if (cm != cam) {
+      flush(cam);
+      cam = cm;
     }
+    const double v = a.partials[(size_t)c * (TPB * 36) + tile * 36 + k];
+    total += v;
+    per_cam += v;
   }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int k = lane + 32 * h;
-    if (k < 36) {
-      a.Hoo[(size_t)i * 36 + k] = oo[h];
-      const int r = k / 6, col = k - 6 * r;
-      if (col == 3) a.go[(size_t)i * 6 + r] = gacc[h];
-    }
-  }
+  if (c0 < c1) flush(cam);
+  if (q == 0) a.Hoo[(size_t)i * 36 + k] = total;
+  if (q == 2 && col == 3) a.go[(size_t)i * 6 + r] = total;
 }
 
 void launch_finalize_side(bool rig, bool epass, const FinalizeSideArgs& a, cudaStream_t s) {
   if (a.n_own == 0) return;
-  const int grid = ceil_div((int64_t)a.n_own * 32, 128);
+  const int grid = a.n_own;
   if (rig) {
-    if (epass) finalize_side_kernel<true, true><<<grid, 128, 0, s>>>(a);
-    else finalize_side_kernel<true, false><<<grid, 128, 0, s>>>(a);
+    if (epass) finalize_side_kernel<true, true><<<grid, 160, 0, s>>>(a);
+    else finalize_side_kernel<true, false><<<grid, 160, 0, s>>>(a);
   } else {
-    if (epass) finalize_side_kernel<false, true><<<grid, 128, 0, s>>>(a);
-    else finalize_side_kernel<false, false><<<grid, 128, 0, s>>>(a);
+    if (epass) finalize_side_kernel<false, true><<<grid, 160, 0, s>>>(a);
+    else finalize_side_kernel<false, false><<<grid, 160, 0, s>>>(a);
   }
   RCC_CUDA(cudaGetLastError());
 }

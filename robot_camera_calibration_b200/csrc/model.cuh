@@ -268,6 +268,113 @@ RCC_HD void eval_corner(const BlockGeom<RIG>& g, const double* __restrict__ sh, 
   }
 }
 
+// Same arithmetic as eval_corner<RIG,true>, but every column group of the two
+// residual rows is handed to `sink` as soon as it is complete, so that a kernel
+// can store it (shared memory) immediately and keep register live ranges short.
+//   sink.shared(i, js[9], r)   sink.marker(i, jm[6])   sink.view(i, jv[6])   sink.ext(i, jx[6])
+// with i = 0 (u row), 1 (v row).  Returns the corner's depth.
+template <bool RIG, class Sink>
+RCC_HD double eval_corner_emit(const BlockGeom<RIG>& g, const double* __restrict__ sh, double ox, double oy,
+                               double pu, double pv, Sink& sink, double& r0, double& r1) {
+  const double fx = sh[0], fy = sh[1], cx = sh[2], cy = sh[3];
+  const double k1 = sh[4], k2 = sh[5], p1 = sh[6], p2 = sh[7], k3 = sh[8];
+  double d[3], P[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    d[i] = g.Rcm[3 * i] * ox + g.Rcm[3 * i + 1] * oy;
+    P[i] = d[i] + g.c0[i];
+  }
+  const double iz = 1.0 / P[2];
+  const double x = P[0] * iz, y = P[1] * iz;
+  const double xx = x * x, yy = y * y, xy = x * y;
+  const double r2 = xx + yy;
+  const double r4 = r2 * r2, r6 = r4 * r2;
+  const double rad = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+  const double tx = 2.0 * xy, ax = r2 + 2.0 * xx, ay = r2 + 2.0 * yy;
+  const double xd = x * rad + p1 * tx + p2 * ax;
+  const double yd = y * rad + p1 * ay + p2 * tx;
+  r0 = fx * xd + cx - pu;
+  r1 = fy * yd + cy - pv;
+  {
+    const double fxx = fx * x, fyy = fy * y;
+    const double js0[9] = {xd, 0.0, 1.0, 0.0, fxx * r2, fxx * r4, fx * tx, fx * ax, fxx * r6};
+    sink.shared(0, js0, r0);
+    const double js1[9] = {0.0, yd, 0.0, 1.0, fyy * r2, fyy * r4, fy * ay, fy * tx, fyy * r6};
+    sink.shared(1, js1, r1);
+  }
+  const double drad = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+  const double dxx = rad + 2.0 * xx * drad + 2.0 * p1 * y + 6.0 * p2 * x;
+  const double dxy = 2.0 * xy * drad + 2.0 * p1 * x + 2.0 * p2 * y;
+  const double dyy = rad + 2.0 * yy * drad + 6.0 * p1 * y + 2.0 * p2 * x;
+  double A[2][3];
+  A[0][0] = fx * dxx * iz;
+  A[0][1] = fx * dxy * iz;
+  A[0][2] = -(A[0][0] * x + A[0][1] * y);
+  A[1][0] = fy * dxy * iz;
+  A[1][1] = fy * dyy * iz;
+  A[1][2] = -(A[1][0] * x + A[1][1] * y);
+
+  double jvt[2][3];  // d/d t_view = -A Mt (kept until the rotation part is ready)
+  {
+    double G[9];
+    cross_mat(d, g.Km, -1.0, G);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double jm[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        jm[j] = A[i][0] * G[j] + A[i][1] * G[3 + j] + A[i][2] * G[6 + j];
+        const double mt = A[i][0] * g.Mt[j] + A[i][1] * g.Mt[3 + j] + A[i][2] * g.Mt[6 + j];
+        jm[3 + j] = mt;
+        jvt[i][j] = -mt;
+      }
+      sink.marker(i, jm);
+    }
+  }
+  if (!RIG) {
+    double G[9];
+    cross_mat(P, g.Jrv, 1.0, G);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double jv[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        jv[j] = A[i][0] * G[j] + A[i][1] * G[3 + j] + A[i][2] * G[6 + j];
+        jv[3 + j] = jvt[i][j];
+      }
+      sink.view(i, jv);
+    }
+  } else {
+    double qb[3], H[9], G[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) qb[i] = g.Rbm[3 * i] * ox + g.Rbm[3 * i + 1] * oy + g.qb0[i];
+    cross_mat(qb, g.Jrv, 1.0, H);
+    mat3_AB(g.RxT, H, G);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double jv[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        jv[j] = A[i][0] * G[j] + A[i][1] * G[3 + j] + A[i][2] * G[6 + j];
+        jv[3 + j] = jvt[i][j];
+      }
+      sink.view(i, jv);
+    }
+    cross_mat(P, g.Jrx, 1.0, G);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double jx[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        jx[j] = A[i][0] * G[j] + A[i][1] * G[3 + j] + A[i][2] * G[6 + j];
+        jx[3 + j] = -(A[i][0] * g.RxT[j] + A[i][1] * g.RxT[3 + j] + A[i][2] * g.RxT[6 + j]);
+      }
+      sink.ext(i, jx);
+    }
+  }
+  return P[2];
+}
+
 // corner k of a tag of half-size hs: bl br tr tl
 RCC_HD void corner_xy(int k, double hs, double& ox, double& oy) {
   ox = (k == 1 || k == 2) ? hs : -hs;

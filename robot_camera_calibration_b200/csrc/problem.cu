@@ -189,7 +189,7 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
   const int32_t* e_of = P->elim_view ? view_idx : marker_idx;
   const int32_t* f_of = P->elim_view ? marker_idx : view_idx;
   const int bpw = P->rig ? PassGeom<true>::BPW : PassGeom<false>::BPW;
-  const int ch_max = std::max(bpw, env_int("RCC_CHUNK", 48));
+  const int ch_max = std::max(bpw, env_int("RCC_CHUNK", 60));
   cudaStream_t s = P->stream;
 
   // ---- E pass order

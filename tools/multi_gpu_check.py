@@ -1,0 +1,41 @@
+"""Under torchrun (N ranks, one GPU each): the N-GPU LM solve must reach the same
+parameters as a single-GPU solve of the whole problem.  Rank 0 prints a JSON line."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from robot_camera_calibration_b200.dist import DistributedBA
+from robot_camera_calibration_b200.problem import BAProblem
+from robot_camera_calibration_b200.scenes import make_scene
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+out = {}
+for name, kw in (("single", dict(n_markers=40, n_views=120, visibility=0.5, seed=41)),
+                 ("rig", dict(n_markers=30, n_views=60, visibility=0.5, n_cam=2, model="rig", seed=42))):
+    kw = dict(kw)
+    scene = make_scene(kw.pop("n_markers"), kw.pop("n_views"), kw.pop("visibility"), **kw)
+    opts = dict(max_iterations=30, function_tolerance=1e-14, gradient_tolerance=1e-12, parameter_tolerance=1e-13)
+    dba = DistributedBA(scene, device=local)
+    summ = dba.solve(**opts)
+    views, markers, intr, dst = dba.gather_parameters()
+    dba.close()
+    if rank == 0:
+        with BAProblem.from_scene(scene, device=local) as gp:
+            s1 = gp.solve(**opts)
+            v1, m1 = gp.get_view_poses(), gp.get_marker_poses()
+            i1, d1 = gp.get_intrinsics()
+        out[name] = dict(iters=(summ["iterations"], s1["iterations"]), cost=(summ["final_cost"], s1["final_cost"]),
+                         dviews=float(np.abs(views - v1).max()), dmarkers=float(np.abs(markers - m1).max()),
+                         dintr=float(np.abs(intr - i1).max()), ddist=float(np.abs(dst - d1).max()),
+                         allreduce_ms=summ["allreduce_ms"])
+    dist.barrier()
+if rank == 0:
+    ok = all(v["dviews"] < 1e-8 and v["dmarkers"] < 1e-8 and v["ddist"] < 1e-8 and
+             abs(v["cost"][0] - v["cost"][1]) <= 1e-10 * v["cost"][1] for v in out.values())
+    print(json.dumps({"world": world, "ok": ok, **out}))
+    if not ok:
+        sys.exit(1)
+dist.destroy_process_group()
