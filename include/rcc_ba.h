@@ -194,6 +194,15 @@ int rcc_ba_flush_l2(rcc_ba_problem* p);
 /* FP64 FMA microbenchmark for the roofline denominator: returns TFLOP/s */
 int rcc_fp64_peak_tflops(int32_t device, double* tflops);
 
+/* ---- batched PnP initialiser (camera_pose.cpp:132-173) ------
+ * For n tags: minimise the reprojection error of the 4 corners over cam_T_tag
+ * (6 dof), the job cv::solvePnP(..., CV_ITERATIVE) does at camera_pose.cpp:163.
+ *   shared9 : fx fy cx cy k1 k2 p1 p2 k3 ;  sizes n ; pixels n x 8
+ *   cam_T_tag (in/out) n x 6 : initial guess in (all-zero => planar homography
+ *   initialisation), refined pose out ; final_cost n (may be NULL; -1 = failed) */
+int rcc_pnp_batch(int32_t device, int64_t n, const double* shared9, const double* sizes, const double* pixels,
+                  double* cam_T_tag, double* final_cost, int32_t max_iterations);
+
 #ifdef __cplusplus
 }
 #endif

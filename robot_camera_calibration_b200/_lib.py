@@ -93,6 +93,8 @@ SIGNATURES = {
     "rcc_ba_synchronize": (C.c_int, [_H]),
     "rcc_ba_flush_l2": (C.c_int, [_H]),
     "rcc_fp64_peak_tflops": (C.c_int, [C.c_int32, c_double_p]),
+    "rcc_pnp_batch": (C.c_int, [C.c_int32, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                C.c_int32]),
 }
 
 _lib = None

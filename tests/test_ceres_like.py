@@ -54,8 +54,8 @@ def test_cost_function_evaluate_layout():
     assert np.allclose(jac[1].reshape(8, 5), Jb["dist"][b], rtol=1e-9, atol=1e-9)
     assert np.allclose(jac[3].reshape(8, 6), Jb["marker"][b], rtol=1e-9, atol=1e-9)
     assert cost.Evaluate(params, residuals, None)                           # residual-only call
-    params[2][0:3] = [0.0, np.pi, 0.0]                                      # camera looks away
-    params[2][3:6] = params[3][3:6] + [0, 0, 1.0]
+    params[2][0:3] = 0.0                                                    # camera axis = world +z ...
+    params[2][3:6] = params[3][3:6] + [0, 0, 1.0]                           # ... and the tag is 1 m behind it
     assert cost.Evaluate(params, residuals, None) is False                  # Evaluate() == false
 
 

@@ -1,0 +1,89 @@
+"""Initialiser: host pose chaining (CPU) and batched GPU PnP against
+cv2.solvePnP / the cv2 restatement of camera_pose.cpp."""
+import numpy as np
+import pytest
+
+from robot_camera_calibration_b200 import initialiser
+from robot_camera_calibration_b200.scenes import compose, invert, make_scene, rodrigues_np
+
+
+def _frames(s, rng=None, drop_world_from=None):
+    frames = []
+    for v in range(len(s.views)):
+        sel = np.nonzero(s.view_idx == v)[0]
+        fr = [(int(s.marker_idx[b]) + 100, float(s.sizes[s.marker_idx[b]]), s.pixels[b].copy()) for b in sel]
+        if v == 0:
+            fr.sort(key=lambda t: t[0] != 100)            # world tag (marker 0) first in frame 0
+        frames.append(fr)
+    return frames
+
+
+def test_chain_poses_follows_the_reference_order():
+    # tags 1,2 in frame 0; frame 1 sees only unknown tags 5,6 (deferred); frame 2 links 2 -> 5
+    I = np.zeros(6)
+    T = lambda x: np.array([0, 0, 0, x, 0, 1.0])
+    frames = [[(1, .1), (2, .1)], [(5, .1), (6, .1)], [(2, .1), (5, .1)]]
+    cTt = [np.stack([T(0), T(1)]), np.stack([T(0), T(2)]), np.stack([T(0), T(3)])]
+    ids, sizes, wTt, wTc = initialiser.chain_poses(frames, cTt)
+    assert ids == [1, 2, 5, 6]                              # 6 is mapped when frame 1 is retried
+    assert np.allclose(wTt[1], T(1) - [0, 0, 0, 0, 0, 1])   # w_T_2 = inv(c_T_1) * c_T_2
+    assert np.allclose(wTc[2][3:], wTt[1][3:] - [0, 0, 1])  # frame 2 referenced through tag 2
+    assert wTc[1] is not None                               # deferred frame resolved by unknownFilepoll
+    # a frame that never links stays unreferenced
+    ids2, _, _, wTc2 = initialiser.chain_poses(frames[:2], cTt[:2])
+    assert wTc2[1] is None and ids2 == [1, 2]
+
+
+def test_world_tag_has_priority_and_last_known_tag_wins():
+    T = lambda x: np.array([0, 0, 0, x, 0, 1.0])
+    frames = [[(1, .1), (2, .1), (3, .1)], [(2, .1), (3, .1), (9, .1)], [(3, .1), (1, .1), (8, .1)]]
+    cTt = [np.stack([T(0), T(1), T(2)]), np.stack([T(0), T(1), T(5)]), np.stack([T(0), T(4), T(6)])]
+    ids, _, wTt, wTc = initialiser.chain_poses(frames, cTt)
+    # frame 1: known tags 2 and 3 -> the last one (3) is the reference (camera_pose.cpp:236-240)
+    assert np.allclose(wTc[1][3], wTt[ids.index(3)][3] - 1)
+    # frame 2: the world tag (1) is present -> used even though tag 3 comes first (:231-235)
+    assert np.allclose(wTc[2][3], 0 - 4)
+
+
+@pytest.mark.gpu
+def test_gpu_pnp_matches_cv2_solvepnp():
+    import cv2
+    s = make_scene(15, 12, 0.8, seed=17)
+    intr, dist = s.truth["intr"][0], s.truth["dist"][0]
+    poses, cost = initialiser.pnp_batch(intr, dist, s.sizes[s.marker_idx], s.pixels)
+    assert (cost >= 0).all()
+    K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
+    worst_r = worst_t = 0.0
+    for b in range(0, s.n_blocks, 7):
+        h = s.sizes[s.marker_idx[b]] / 2
+        obj = np.array([[-h, -h, 0], [h, -h, 0], [h, h, 0], [-h, h, 0]], float)
+        ok, rvec, tvec = cv2.solvePnP(obj, s.pixels[b].reshape(4, 2), K, dist, flags=cv2.SOLVEPNP_ITERATIVE)
+        Rg, Rc = rodrigues_np(poses[b, :3]), rodrigues_np(rvec.ravel())
+        worst_r = max(worst_r, np.abs(Rg - Rc).max())
+        worst_t = max(worst_t, np.abs(poses[b, 3:] - tvec.ravel()).max())
+    # both minimise the same 8-residual cost; OpenCV stops at its own tolerance
+    assert worst_r < 1e-4 and worst_t < 1e-4
+    # sanity against ground truth: 0.3 px noise on a ~15 px tag leaves decimetre depth errors at most
+    truth = compose(invert(s.truth["views"][s.view_idx]), s.truth["markers"][s.marker_idx])
+    assert np.median(np.abs(poses[:, 3:] - truth[:, 3:])) < 0.02
+
+
+@pytest.mark.gpu
+def test_initialise_matches_the_cv2_restatement_and_feeds_ba():
+    import pnp_oracle
+    from robot_camera_calibration_b200.problem import BAProblem
+    s = make_scene(12, 20, 0.6, seed=19)
+    frames = _frames(s)
+    intr, dist = s.truth["intr"][0], s.truth["dist"][0]
+    scene, ids, kept = initialiser.initialise(frames, intr, dist)
+    o_ids, o_sizes, o_wTt, o_wTc = pnp_oracle.initialise(frames, intr, dist)
+    assert list(ids) == list(o_ids)
+    assert list(kept) == [n for n, t in enumerate(o_wTc) if t is not None]
+    assert np.abs(rodrigues_np(scene.markers[:, :3]) - rodrigues_np(o_wTt[:, :3])).max() < 1e-3
+    assert np.abs(scene.markers[:, 3:] - o_wTt[:, 3:]).max() < 1e-3
+    # the initial guess is good enough for the bundle adjustment to converge
+    scene.const_intr[:] = True
+    scene.const_dist[:] = True
+    with BAProblem.from_scene(scene) as p:
+        summ = p.solve(max_iterations=30)
+    assert summ["final_cost"] < 0.1 * summ["initial_cost"] or summ["final_cost"] < 1.0 * scene.n_blocks
