@@ -52,6 +52,7 @@ enum rcc_status {
 
 enum rcc_model { RCC_MODEL_SINGLE = 0, RCC_MODEL_RIG = 1 };
 enum rcc_eliminate { RCC_ELIM_AUTO = 0, RCC_ELIM_VIEWS = 1, RCC_ELIM_MARKERS = 2 };
+enum rcc_loss { RCC_LOSS_TRIVIAL = 0, RCC_LOSS_HUBER = 1, RCC_LOSS_CAUCHY = 2 };
 enum rcc_block_kind { RCC_BLOCK_VIEW = 0, RCC_BLOCK_MARKER = 1, RCC_BLOCK_INTR = 2, RCC_BLOCK_DIST = 3, RCC_BLOCK_EXT = 4 };
 
 typedef struct {
@@ -114,6 +115,10 @@ int rcc_ba_set_observations(rcc_ba_problem* p, const int32_t* view_idx, const in
 int rcc_ba_update_pixels(rcc_ba_problem* p, const double* pixels /*n_obs_blocks x 8*/);
 /* hold a parameter block constant (the gauge: world tag, camera_pose.cpp:71-80) */
 int rcc_ba_set_constant(rcc_ba_problem* p, int32_t block_kind, int32_t index, int32_t is_constant);
+
+/* robust loss rho(s) on s = ||r||^2 of each tag's 8-residual block (Ceres LossFunction semantics:
+ * HuberLoss(scale) / CauchyLoss(scale), scale in pixels); the reported cost becomes 0.5 * sum rho(s) */
+int rcc_ba_set_loss(rcc_ba_problem* p, int32_t loss, double scale);
 
 int rcc_ba_get_intrinsics(rcc_ba_problem* p, double* intr, double* dist);
 int rcc_ba_get_rig_extrinsics(rcc_ba_problem* p, double* ext);

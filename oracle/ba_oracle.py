@@ -76,6 +76,7 @@ class OracleProblem:
         self.const_intr = z(const_intr, nc)
         self.const_dist = z(const_dist, nc)
         self.const_ext = z(const_ext, nc) if model == "rig" else np.ones(nc, bool)
+        self.loss, self.loss_scale = None, 1.0     # None | "huber" | "cauchy" (per tag residual block)
 
     # ---- global parameter vector layout: [views | markers | per-cam (intr4 dist5 [ext6])]
     @property
@@ -126,6 +127,11 @@ class OracleProblem:
         return m
 
     def copy(self):
+        q = self._copy()
+        q.loss, q.loss_scale = self.loss, self.loss_scale
+        return q
+
+    def _copy(self):
         return OracleProblem(self.model, self.intr, self.dist, self.ext, self.views,
                              self.markers, self.sizes, self.view_idx, self.marker_idx,
                              self.cam_idx, self.pixels, self.const_views,
@@ -216,9 +222,26 @@ def depths(p):
     return z
 
 
+def robust(p, r):
+    """Per-block (sqrt(rho'(s)), rho(s)) with s = ||r_block||^2 -- Ceres LossFunction
+    semantics (HuberLoss / CauchyLoss with scale a); rho'' <= 0 for both, so the
+    corrected residuals / Jacobian rows are simply scaled by sqrt(rho')."""
+    s = (r * r).sum(1)
+    a2 = p.loss_scale ** 2
+    if p.loss == "huber":
+        rt = np.sqrt(np.maximum(s, 1e-300))
+        rho = np.where(s <= a2, s, 2 * p.loss_scale * rt - a2)
+        rho1 = np.where(s <= a2, 1.0, p.loss_scale / rt)
+    elif p.loss == "cauchy":
+        rho, rho1 = a2 * np.log1p(s / a2), 1.0 / (1.0 + s / a2)
+    else:
+        rho, rho1 = s, np.ones_like(s)
+    return np.sqrt(rho1), rho
+
+
 def cost(p):
     r = residuals(p)
-    return 0.5 * float((r * r).sum())
+    return 0.5 * float(robust(p, r)[1].sum())
 
 
 def local_param_names(model):
@@ -334,8 +357,11 @@ def dense_jacobian(p, Jb=None):
 def normal_equations(p):
     """H = J^T J, g = J^T r, cost -- dense, constant blocks NOT yet masked."""
     J = dense_jacobian(p)
-    r = residuals(p).ravel()
-    return J.T @ J, J.T @ r, 0.5 * float(r @ r)
+    r = residuals(p)
+    w, rho = robust(p, r)
+    J = J * np.repeat(w, 8)[:, None]
+    r = (r * w[:, None]).ravel()
+    return J.T @ J, J.T @ r, 0.5 * float(rho.sum())
 
 
 def lm_diagonal(H, radius, min_diag=1e-6, max_diag=1e32):

@@ -68,6 +68,7 @@ SIGNATURES = {
     "rcc_ba_set_observations": (C.c_int, [_H, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
     "rcc_ba_update_pixels": (C.c_int, [_H, c_double_p]),
     "rcc_ba_set_constant": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32]),
+    "rcc_ba_set_loss": (C.c_int, [_H, C.c_int32, C.c_double]),
     "rcc_ba_get_intrinsics": (C.c_int, [_H, c_double_p, c_double_p]),
     "rcc_ba_get_rig_extrinsics": (C.c_int, [_H, c_double_p]),
     "rcc_ba_get_view_poses": (C.c_int, [_H, c_double_p]),

@@ -60,6 +60,22 @@ class TagReprojectionCost:
         return not out["failed"]
 
 
+class HuberLoss:
+    """ceres::HuberLoss(a): rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond."""
+    kind = "huber"
+
+    def __init__(self, a):
+        self.a = float(a)
+
+
+class CauchyLoss:
+    """ceres::CauchyLoss(a): rho(s) = a^2 log(1 + s / a^2)."""
+    kind = "cauchy"
+
+    def __init__(self, a):
+        self.a = float(a)
+
+
 class SolverOptions:
     def __init__(self, max_num_iterations=50, initial_trust_region_radius=1e4, max_trust_region_radius=1e16,
                  min_relative_decrease=1e-3, function_tolerance=1e-6, gradient_tolerance=1e-10,
@@ -92,6 +108,7 @@ class Problem:
         self._blocks = []            # (cost, intr, dist, view, marker, ext)
         self._const = set()
         self._known = {}
+        self._loss = None
 
     # -- Ceres names --------------------------------------------------------
     def AddParameterBlock(self, values, size=None):
@@ -100,8 +117,10 @@ class Problem:
         return a
 
     def AddResidualBlock(self, cost_function, loss_function, *parameter_blocks):
-        if loss_function is not None:
-            raise NotImplementedError("only the trivial loss is implemented on this path")
+        key = None if loss_function is None else (loss_function.kind, loss_function.a)
+        if self._blocks and key != self._loss:
+            raise NotImplementedError("all residual blocks must share one loss function on this path")
+        self._loss = key
         sizes = cost_function.parameter_block_sizes()
         if len(parameter_blocks) != len(sizes):
             raise ValueError(f"expected {len(sizes)} parameter blocks, got {len(parameter_blocks)}")
@@ -170,6 +189,8 @@ class Problem:
         gp.set_marker_poses(np.stack(mlist))
         gp.set_marker_sizes([sizes[m] for m in range(len(mlist))])
         gp.set_observations(vi, mi, ci, np.stack(px))
+        if self._loss is not None:
+            gp.set_loss(*self._loss)
         for i, a in enumerate(vlist):
             if id(a) in self._const:
                 gp.set_constant("view", i)

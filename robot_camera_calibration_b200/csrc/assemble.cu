@@ -31,18 +31,20 @@ namespace rcc {
 template <bool RIG, bool OWN_IS_VIEW>
 struct RowSink {
   double* row[2];
+  double w;     // row scale sqrt(rho'(s)) of the block (1 for the trivial loss)
+  double c22;   // sqrt(rho(s)) on the block's first row, 0 elsewhere: S2S2[4][4] sums the robust cost
   __device__ __forceinline__ void put6(int i, int col, const double* v) {
     double2* d = reinterpret_cast<double2*>(row[i] + col);
-    d[0] = make_double2(v[0], v[1]);
-    d[1] = make_double2(v[2], v[3]);
-    d[2] = make_double2(v[4], v[5]);
+    d[0] = make_double2(w * v[0], w * v[1]);
+    d[1] = make_double2(w * v[2], w * v[3]);
+    d[2] = make_double2(w * v[4], w * v[5]);
   }
   __device__ __forceinline__ void shared(int i, const double* js, double r) {
     put6(i, 12, js);
     double2* d = reinterpret_cast<double2*>(row[i] + 18);
-    d[0] = make_double2(js[6], js[7]);
-    d[1] = make_double2(js[8], r);
-    d[2] = make_double2(0.0, 0.0);
+    d[0] = make_double2(w * js[6], w * js[7]);
+    d[1] = make_double2(w * js[8], w * r);
+    d[2] = make_double2(i == 0 ? c22 : 0.0, 0.0);
   }
   __device__ __forceinline__ void marker(int i, const double* jm) { put6(i, OWN_IS_VIEW ? 6 : 0, jm); }
   __device__ __forceinline__ void view(int i, const double* jv) { put6(i, OWN_IS_VIEW ? 0 : 6, jv); }
@@ -70,7 +72,7 @@ struct WarpSmem {
   static constexpr int TOTAL = CONSTS + 2 * POSEX + 16;
 };
 
-template <bool RIG, bool EPASS, bool OWN_IS_VIEW>
+template <bool RIG, bool EPASS, bool OWN_IS_VIEW, bool LOSS>
 __global__ void __launch_bounds__(PassGeom<RIG>::WARPS * 32, RCC_K2_MIN_CTAS)
 assemble_kernel(const AssembleArgs a) {
   using PG = PassGeom<RIG>;
@@ -147,15 +149,37 @@ assemble_kernel(const AssembleArgs a) {
         px_nxt = *reinterpret_cast<const double2*>(a.pix + (g + BPW) * 8 + 2 * t);
     }
     // ---- phase 1: corner evaluation ---------------------------------------
+    const double* ox_rec = stage + (buf * BPW + min(b, BPW - 1)) * POSEX;
+    const double* vx = OWN_IS_VIEW ? own_x : ox_rec;
+    const double* mx = OWN_IS_VIEW ? ox_rec : own_x;
+    BlockGeom<RIG> geo;
+    double ox = 0.0, oy = 0.0;
     if (valid && eval_lane) {
-      const double* ox_rec = stage + (buf * BPW + b) * POSEX;
-      const double* vx = OWN_IS_VIEW ? own_x : ox_rec;
-      const double* mx = OWN_IS_VIEW ? ox_rec : own_x;
-      BlockGeom<RIG> geo;
       block_geometry<RIG>(vx, mx, RIG ? ext_x : nullptr, geo);
-      double ox, oy;
       corner_xy(t, mx[PX_HS], ox, oy);
-      RowSink<RIG, OWN_IS_VIEW> sink{blk + (2 * t) * NCOL, blk + (2 * t + 1) * NCOL};
+    }
+    double w = 1.0, c22 = 0.0;
+    if (LOSS) {
+      // s = sum of the 8 squared residuals of the block: residual-only evaluation, then a
+      // 4-lane gather over the block's corner lanes (every lane of the warp takes part)
+      double s_own = 0.0;
+      if (valid && eval_lane) {
+        CornerRows<RIG> c;
+        eval_corner<RIG, false>(geo, sh, ox, oy, px.x, px.y, c);
+        s_own = c.r[0] * c.r[0] + c.r[1] * c.r[1];
+      }
+      const int l0 = min(b, BPW - 1) * TPB;
+      double s_blk = __shfl_sync(0xffffffffu, s_own, l0);
+      s_blk += __shfl_sync(0xffffffffu, s_own, l0 + 1);
+      s_blk += __shfl_sync(0xffffffffu, s_own, l0 + 2);
+      s_blk += __shfl_sync(0xffffffffu, s_own, l0 + 3);
+      double rho1;
+      const double rho = robust_rho(a.loss, a.loss_a2, s_blk, rho1);
+      w = sqrt(rho1);
+      c22 = (t == 0) ? sqrt(fmax(rho, 0.0)) : 0.0;
+    }
+    if (valid && eval_lane) {
+      RowSink<RIG, OWN_IS_VIEW> sink{{blk + (2 * t) * NCOL, blk + (2 * t + 1) * NCOL}, w, c22};
       double r0, r1;
       const double depth = eval_corner_emit<RIG>(geo, sh, ox, oy, px.x, px.y, sink, r0, r1);
       if (!(depth > 0.0) || !isfinite(r0) || !isfinite(r1)) *a.fail_flag = 1;
@@ -204,12 +228,12 @@ assemble_kernel(const AssembleArgs a) {
   }
 }
 
-template <bool RIG, bool EPASS, bool OWN_IS_VIEW>
+template <bool RIG, bool EPASS, bool OWN_IS_VIEW, bool LOSS>
 static void launch_assemble_t(const AssembleArgs& a, cudaStream_t s) {
   using PG = PassGeom<RIG>;
   if (a.n_chunks == 0) return;
   const size_t smem = PG::WARPS * WarpSmem<RIG>::TOTAL * sizeof(double);
-  auto k = assemble_kernel<RIG, EPASS, OWN_IS_VIEW>;
+  auto k = assemble_kernel<RIG, EPASS, OWN_IS_VIEW, LOSS>;
   static bool attr_set = false;
   if (!attr_set) {
     RCC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -220,18 +244,24 @@ static void launch_assemble_t(const AssembleArgs& a, cudaStream_t s) {
   RCC_CUDA(cudaGetLastError());
 }
 
-void launch_assemble(bool rig, bool epass, bool own_is_view, const AssembleArgs& a, cudaStream_t s) {
+template <bool LOSS>
+static void launch_assemble_l(bool rig, bool epass, bool own_is_view, const AssembleArgs& a, cudaStream_t s) {
   const int sel = (rig ? 4 : 0) | (epass ? 2 : 0) | (own_is_view ? 1 : 0);
   switch (sel) {
-    case 0: launch_assemble_t<false, false, false>(a, s); break;
-    case 1: launch_assemble_t<false, false, true>(a, s); break;
-    case 2: launch_assemble_t<false, true, false>(a, s); break;
-    case 3: launch_assemble_t<false, true, true>(a, s); break;
-    case 4: launch_assemble_t<true, false, false>(a, s); break;
-    case 5: launch_assemble_t<true, false, true>(a, s); break;
-    case 6: launch_assemble_t<true, true, false>(a, s); break;
-    default: launch_assemble_t<true, true, true>(a, s); break;
+    case 0: launch_assemble_t<false, false, false, LOSS>(a, s); break;
+    case 1: launch_assemble_t<false, false, true, LOSS>(a, s); break;
+    case 2: launch_assemble_t<false, true, false, LOSS>(a, s); break;
+    case 3: launch_assemble_t<false, true, true, LOSS>(a, s); break;
+    case 4: launch_assemble_t<true, false, false, LOSS>(a, s); break;
+    case 5: launch_assemble_t<true, false, true, LOSS>(a, s); break;
+    case 6: launch_assemble_t<true, true, false, LOSS>(a, s); break;
+    default: launch_assemble_t<true, true, true, LOSS>(a, s); break;
   }
+}
+
+void launch_assemble(bool rig, bool epass, bool own_is_view, const AssembleArgs& a, cudaStream_t s) {
+  if (a.loss != 0) launch_assemble_l<true>(rig, epass, own_is_view, a, s);
+  else launch_assemble_l<false>(rig, epass, own_is_view, a, s);
 }
 
 // ---------------------------------------------------------------------------
@@ -372,7 +402,8 @@ __global__ void __launch_bounds__(256) finalize_shared_final_kernel(const Finali
   // S2 x S2
   if (r < 3 && q < 3) H[(size_t)(base + 6 + r) * ns + base + 6 + q] = tile[2][tid];
   else if (r < 3 && q == 3) a.gs[base + 6 + r] = tile[2][tid];
-  else if (r == 3 && q == 3) a.cost2_cam[cam] = tile[2][tid];
+  else if (!a.robust && r == 3 && q == 3) a.cost2_cam[cam] = tile[2][tid];
+  else if (a.robust && r == 4 && q == 4) a.cost2_cam[cam] = tile[2][tid];
   if (RIG) {
     // S1 x X
     H[(size_t)(base + r) * ns + base + 9 + q] = tile[3][tid];

@@ -89,6 +89,13 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a
       }
     }
   }
+  if (a.loss != 0) {
+    // the 4 corner threads of a tag are adjacent lanes: rho(sum of the 8 squared residuals) / 4 each
+    double sb = r2 + __shfl_xor_sync(0xffffffffu, r2, 1);
+    sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+    double rho1;
+    r2 = (g < a.n) ? 0.25 * robust_rho(a.loss, a.loss_a2, sb, rho1) : 0.0;
+  }
   const double s = block_sum(r2, red);
   if (threadIdx.x == 0 && a.cost2_partials) a.cost2_partials[blockIdx.x] = s;
 }

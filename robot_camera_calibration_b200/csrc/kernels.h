@@ -81,6 +81,8 @@ struct AssembleArgs {
   double* partials;       // [n_chunks * TPB * 36]
   double* W;              // [n*36] (E pass only) row-major 6x6: rows own, cols other
   int32_t* fail_flag;     // set to 1 on depth <= 0 / non-finite residual
+  int32_t loss;           // 0 trivial, 1 Huber, 2 Cauchy (per tag residual block)
+  double loss_a2;         // squared loss scale
 };
 
 // K2: fused residual + Jacobian + J^T J tiles.  own_is_view tells which pose
@@ -114,6 +116,7 @@ struct FinalizeSharedArgs {
   double* gs;                   // [n_shared]
   double* cost2_cam;            // [n_cam] sum r^2 per camera
   double* scratch;              // [n_cam * FIN_SLICES * 6 * 36] first-stage partial tiles
+  int32_t robust;               // 1: cost slot is S2S2[4][4] (sum rho), else S2S2[3][3] (sum r^2)
 };
 constexpr int FIN_SLICES = 64;  // CTAs per camera in the first stage of finalize_shared
 void launch_finalize_shared(bool rig, const FinalizeSharedArgs& a, cudaStream_t s);
@@ -145,8 +148,10 @@ struct EvalArgs {
   double* jac_view;         // [n*8*6]
   double* jac_marker;       // [n*8*6]
   double* jac_ext;          // [n*8*6]
-  double* cost2_partials;   // [grid] sum r^2 per CTA
+  double* cost2_partials;   // [grid] sum rho(||r_block||^2) per CTA
   int32_t* fail_flag;
+  int32_t loss;
+  double loss_a2;
 };
 int eval_grid(int64_t n);   // CTAs launch_evaluate / launch_cost will use
 void launch_evaluate(bool rig, bool want_jac, const EvalArgs& a, cudaStream_t s);

@@ -375,6 +375,26 @@ RCC_HD double eval_corner_emit(const BlockGeom<RIG>& g, const double* __restrict
   return P[2];
 }
 
+// Robust loss rho(s) on s = ||r_block||^2 (all 8 residuals of a tag), Ceres semantics:
+// the corrected Gauss-Newton model scales residuals and Jacobian rows of the block by
+// sqrt(rho'(s)) (for Huber and Cauchy rho'' <= 0, so Ceres's alpha is 0) and the cost is
+// 0.5 * rho(s).   loss: 0 trivial, 1 Huber(a), 2 Cauchy(a);  a2 = a * a.
+RCC_HD double robust_rho(int loss, double a2, double s, double& rho1) {
+  if (loss == 1) {
+    if (s <= a2) { rho1 = 1.0; return s; }
+    const double r = sqrt(s), a = sqrt(a2);
+    rho1 = a / r;
+    return 2.0 * a * r - a2;
+  }
+  if (loss == 2) {
+    const double q = 1.0 + s / a2;
+    rho1 = 1.0 / q;
+    return a2 * log(q);
+  }
+  rho1 = 1.0;
+  return s;
+}
+
 // corner k of a tag of half-size hs: bl br tr tl
 RCC_HD void corner_xy(int k, double hs, double& ox, double& oy) {
   ox = (k == 1 || k == 2) ? hs : -hs;

@@ -370,6 +370,8 @@ static void do_linearize(P_t* P) {
   a.shared = P->shared.p;
   a.sizes = P->sizes.p;
   a.fail_flag = P->fail_flag.p;
+  a.loss = P->loss;
+  a.loss_a2 = P->loss_scale * P->loss_scale;
   {
     Scoped t(P, ST_ASSEMBLE_E, 1);
     a.oth = P->e_oth.p;
@@ -397,7 +399,8 @@ static void do_linearize(P_t* P) {
     FinalizeSideArgs ff{P->part_f.p, P->f_chunks.p, P->f_chunk_ptr.p, P->n_f, P->n_shared, P->Hff.p, P->gf.p, P->Hfs.p};
     launch_finalize_side(P->rig, false, ff, P->stream);
     FinalizeSharedArgs fs{P->part_e.p, P->part_f.p, P->cam_chunks_e.p, P->cam_ptr_e.p, P->cam_chunks_f.p,
-                          P->cam_ptr_f.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p, P->fin_scratch.p};
+                          P->cam_ptr_f.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p, P->fin_scratch.p,
+                          P->loss != 0 ? 1 : 0};
     launch_finalize_shared(P->rig, fs, P->stream);
   }
   P->linearized = true;
@@ -535,6 +538,8 @@ static EvalArgs eval_args(P_t* P, bool cand) {
   a.sizes = P->sizes.p;
   a.cost2_partials = P->cost_partials.p;
   a.fail_flag = P->fail_flag.p;
+  a.loss = P->loss;
+  a.loss_a2 = P->loss_scale * P->loss_scale;
   return a;
 }
 
@@ -925,6 +930,16 @@ int rcc_ba_set_constant(rcc_ba_problem* P, int32_t kind, int32_t index, int32_t 
   (*v)[index] = is_constant ? 1 : 0;
   P->const_dirty = true;
   P->schur_done = P->step_ready = P->cand_ready = false;
+  API_END(P)
+}
+
+int rcc_ba_set_loss(rcc_ba_problem* P, int32_t loss, double scale) {
+  API_BEGIN(P)
+  RCC_REQUIRE(loss >= RCC_LOSS_TRIVIAL && loss <= RCC_LOSS_CAUCHY, RCC_BAD_ARG, "unknown loss");
+  RCC_REQUIRE(loss == RCC_LOSS_TRIVIAL || scale > 0.0, RCC_BAD_ARG, "loss scale must be positive");
+  P->loss = loss;
+  P->loss_scale = scale;
+  P->linearized = P->schur_done = P->step_ready = P->cand_ready = false;
   API_END(P)
 }
 

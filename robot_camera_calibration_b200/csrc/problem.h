@@ -86,6 +86,8 @@ struct rcc_ba_problem {
 
   bool have_obs = false, linearized = false, schur_done = false, step_ready = false, cand_ready = false;
   double min_diag = 1e-6, max_diag = 1e32;
+  int loss = 0;
+  double loss_scale = 1.0;
   rcc::StageTimer timer;
   rcc::DBuf<double> flush_buf;
 

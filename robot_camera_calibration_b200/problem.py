@@ -137,6 +137,11 @@ class BAProblem:
                     "dist": L.BLOCK_DIST, "ext": L.BLOCK_EXT}[kind]
         self._check(self.lib.rcc_ba_set_constant(self.h, kind, index, int(bool(is_constant))))
 
+    def set_loss(self, loss, scale=1.0):
+        """loss: 'trivial' | 'huber' | 'cauchy' on each tag's 8-residual block (scale in pixels)."""
+        code = {"trivial": 0, "huber": 1, "cauchy": 2}[loss] if isinstance(loss, str) else int(loss)
+        self._check(self.lib.rcc_ba_set_loss(self.h, code, float(scale)))
+
     # ------------------------------------------------------------------ getters
     def get_intrinsics(self):
         intr, dist = np.empty((self.n_cameras, 4)), np.empty((self.n_cameras, 5))

@@ -51,7 +51,8 @@ def oracle_blocks(p, elim_view):
     # per-observation cross blocks W = J_e^T J_f
     Jb = O.jacobian_blocks_cs(p)
     Je, Jf = (Jb["view"], Jb["marker"]) if elim_view else (Jb["marker"], Jb["view"])
-    out["W"] = np.einsum('nri,nrj->nij', Je, Jf)
+    w, _ = O.robust(p, O.residuals(p))
+    out["W"] = np.einsum('nri,nrj->nij', Je, Jf) * (w * w)[:, None, None]
     return out
 
 

@@ -179,3 +179,44 @@ def test_gpu_matches_committed_golden_vectors(name):
             mcc, step_norm, _ = gp.solve_step()
             assert abs(step_norm - np.linalg.norm(g["delta"])) <= 1e-6 * np.linalg.norm(g["delta"])
             assert abs(mcc - float(g["mcc"])) <= 1e-6 * abs(float(g["mcc"]))
+
+
+@pytest.mark.parametrize("loss,scale", [("huber", 2.0), ("cauchy", 3.0)])
+@pytest.mark.parametrize("name", ["single", "rig"])
+def test_robust_loss_matches_oracle(name, loss, scale):
+    """Huber / Cauchy on each tag's 8-residual block (Ceres Corrector with alpha = 0)."""
+    s = _scene(name)
+    rng = np.random.default_rng(5)
+    bad = rng.choice(s.n_blocks, 12, replace=False)
+    s.pixels[bad] += rng.normal(0, 25.0, (12, 8))            # gross outliers
+    p = to_oracle(s)
+    p.loss, p.loss_scale = loss, scale
+    ob = oracle_blocks(p, True)
+    S, b, *_ = oracle_reduced(p, True, 1e4)
+    with BAProblem.from_scene(s, eliminate="views") as gp:
+        gp.set_loss(loss, scale)
+        out = gp.evaluate(want_jacobians=False)
+        cost = gp.linearize()
+        nb = gp.normal_blocks()
+        gp.schur(1e4)
+        Sg, bg = gp.reduced_system()
+    assert abs(out["cost"] - ob["cost"]) <= TOL * ob["cost"]          # 0.5 * sum rho(s)
+    assert abs(cost - ob["cost"]) <= TOL * ob["cost"]
+    for k in ("Hee", "Hff", "W", "ge", "gf", "Hes", "Hfs"):
+        assert max_block_rel(nb[k], ob[k], floor=1e-6 * np.abs(ob[k]).max()) < TOL, k
+    assert rel_fro(nb["Hss"], ob["Hss"]) < TOL and rel_fro(nb["gs"], ob["gs"]) < TOL
+    assert rel_fro(Sg, S) < TOL and rel_fro(bg, b) < TOL
+
+
+def test_huber_resists_outliers():
+    s = make_scene(10, 30, 0.8, seed=23, pixel_noise=0.1)
+    rng = np.random.default_rng(1)
+    bad = rng.choice(s.n_blocks, s.n_blocks // 20, replace=False)
+    s.pixels[bad] += rng.normal(0, 40.0, (len(bad), 8))
+    err = {}
+    for loss in ("trivial", "huber"):
+        with BAProblem.from_scene(s) as gp:
+            gp.set_loss(loss, 1.0)
+            gp.solve(max_iterations=60)
+            err[loss] = np.abs(gp.get_marker_poses()[:, 3:] - s.truth["markers"][:, 3:]).max()
+    assert err["huber"] < 0.5 * err["trivial"]
