@@ -28,13 +28,38 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;  // valid on thread 0
 }
 
+// per-block staging record (doubles): res[8] | intr[8][4] | dist[8][5] | view[8][6] | marker[8][6] | ext[8][6]
+template <bool RIG>
+struct EvalRec {
+  static constexpr int RES = 0, JI = 8, JD = 40, JV = 80, JM = 128, JX = 176;
+  static constexpr int SIZE = RIG ? 226 : 178;   // +2: consecutive records shift by 16 B across the smem banks
+};
+
+// cooperative, coalesced copy-out of one output array for the 8 blocks of a warp:
+// K doubles per block, contiguous in global memory per block (caller order via orig)
+template <int K, int REC>
+__device__ __forceinline__ void copy_out(double* __restrict__ dst, const double* wrec, int off, const int64_t* o8,
+                                         int nblk, int lane) {
+  constexpr int PIECES = K / 2;  // 16-byte pieces per block
+  for (int idx = lane; idx < nblk * PIECES; idx += 32) {
+    const int q = idx / PIECES, pc = idx - q * PIECES;
+    const double2 v = *reinterpret_cast<const double2*>(wrec + q * REC + off + 2 * pc);
+    *reinterpret_cast<double2*>(dst + o8[q] * K + 2 * pc) = v;
+  }
+}
+
 template <bool RIG, bool WANT_J>
 __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a) {
+  using ER = EvalRec<RIG>;
   __shared__ double red[EVAL_THREADS / 32];
+  extern __shared__ __align__(16) double stage[];   // WANT_J: [warps][8 blocks][ER::SIZE]; [warps][8] caller positions
   const int64_t tid = (int64_t)blockIdx.x * EVAL_THREADS + threadIdx.x;
   const int64_t g = tid >> 2;
   const int t = (int)(tid & 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double r2 = 0.0;
+  double* wrec = WANT_J ? stage + (size_t)warp * 8 * ER::SIZE : nullptr;
+  int64_t* wpos = WANT_J ? reinterpret_cast<int64_t*>(stage + (size_t)(EVAL_THREADS / 32) * 8 * ER::SIZE) + warp * 8 : nullptr;
   if (g < a.n) {
     const int vi = a.view_idx[g], mi = a.marker_idx[g], cam = a.cam[g];
     constexpr int SP = RIG ? 15 : 9;
@@ -49,44 +74,55 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a
     if (!(c.depth > 0.0) || !isfinite(c.r[0]) || !isfinite(c.r[1])) *a.fail_flag = 1;
     r2 = c.r[0] * c.r[0] + c.r[1] * c.r[1];
     const int64_t o = a.orig ? (int64_t)a.orig[g] : g;
-    if (a.residuals) *reinterpret_cast<double2*>(a.residuals + o * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
-    if (WANT_J) {
-      if (a.jac_intr) {
-        double2* d = reinterpret_cast<double2*>(a.jac_intr + o * 32 + 8 * t);
-        d[0] = make_double2(c.js[0][0], c.js[0][1]);
-        d[1] = make_double2(c.js[0][2], c.js[0][3]);
-        d[2] = make_double2(c.js[1][0], c.js[1][1]);
-        d[3] = make_double2(c.js[1][2], c.js[1][3]);
-      }
-      if (a.jac_dist) {
-        double2* d = reinterpret_cast<double2*>(a.jac_dist + o * 40 + 10 * t);
-        d[0] = make_double2(c.js[0][4], c.js[0][5]);
-        d[1] = make_double2(c.js[0][6], c.js[0][7]);
-        d[2] = make_double2(c.js[0][8], c.js[1][4]);
-        d[3] = make_double2(c.js[1][5], c.js[1][6]);
-        d[4] = make_double2(c.js[1][7], c.js[1][8]);
-      }
-      if (a.jac_view) {
-        double2* d = reinterpret_cast<double2*>(a.jac_view + o * 48 + 12 * t);
+    if (!WANT_J) {
+      if (a.residuals) *reinterpret_cast<double2*>(a.residuals + o * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
+    } else {
+      // stage the corner's two rows of every block in Ceres layout
+      double* rec = wrec + (lane >> 2) * ER::SIZE;
+      if (t == 0) wpos[lane >> 2] = o;
+      *reinterpret_cast<double2*>(rec + ER::RES + 2 * t) = make_double2(c.r[0], c.r[1]);
+      double2* d = reinterpret_cast<double2*>(rec + ER::JI + 8 * t);
+      d[0] = make_double2(c.js[0][0], c.js[0][1]);
+      d[1] = make_double2(c.js[0][2], c.js[0][3]);
+      d[2] = make_double2(c.js[1][0], c.js[1][1]);
+      d[3] = make_double2(c.js[1][2], c.js[1][3]);
+      d = reinterpret_cast<double2*>(rec + ER::JD + 10 * t);
+      d[0] = make_double2(c.js[0][4], c.js[0][5]);
+      d[1] = make_double2(c.js[0][6], c.js[0][7]);
+      d[2] = make_double2(c.js[0][8], c.js[1][4]);
+      d[3] = make_double2(c.js[1][5], c.js[1][6]);
+      d[4] = make_double2(c.js[1][7], c.js[1][8]);
+      d = reinterpret_cast<double2*>(rec + ER::JV + 12 * t);
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jv[i][2 * j], c.jv[i][2 * j + 1]);
-      }
-      if (a.jac_marker) {
-        double2* d = reinterpret_cast<double2*>(a.jac_marker + o * 48 + 12 * t);
+        for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jv[i][2 * j], c.jv[i][2 * j + 1]);
+      d = reinterpret_cast<double2*>(rec + ER::JM + 12 * t);
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jm[i][2 * j], c.jm[i][2 * j + 1]);
-      }
-      if (RIG && a.jac_ext) {
-        double2* d = reinterpret_cast<double2*>(a.jac_ext + o * 48 + 12 * t);
+        for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jm[i][2 * j], c.jm[i][2 * j + 1]);
+      if (RIG) {
+        d = reinterpret_cast<double2*>(rec + ER::JX + 12 * t);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jx[i][2 * j], c.jx[i][2 * j + 1]);
       }
+    }
+  }
+  if (WANT_J) {
+    __syncwarp();
+    // blocks of this warp: g0 .. g0+7 (clipped)
+    const int64_t g0 = ((int64_t)blockIdx.x * EVAL_THREADS + warp * 32) >> 2;
+    const int nblk = (int)max((int64_t)0, min((int64_t)8, a.n - g0));
+    if (nblk > 0) {
+      if (a.residuals) copy_out<8, ER::SIZE>(a.residuals, wrec, ER::RES, wpos, nblk, lane);
+      if (a.jac_intr) copy_out<32, ER::SIZE>(a.jac_intr, wrec, ER::JI, wpos, nblk, lane);
+      if (a.jac_dist) copy_out<40, ER::SIZE>(a.jac_dist, wrec, ER::JD, wpos, nblk, lane);
+      if (a.jac_view) copy_out<48, ER::SIZE>(a.jac_view, wrec, ER::JV, wpos, nblk, lane);
+      if (a.jac_marker) copy_out<48, ER::SIZE>(a.jac_marker, wrec, ER::JM, wpos, nblk, lane);
+      if (RIG && a.jac_ext) copy_out<48, ER::SIZE>(a.jac_ext, wrec, ER::JX, wpos, nblk, lane);
     }
   }
   if (a.loss != 0) {
@@ -100,17 +136,30 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a
   if (threadIdx.x == 0 && a.cost2_partials) a.cost2_partials[blockIdx.x] = s;
 }
 
+template <bool RIG, bool WANT_J>
+static void launch_evaluate_t(const EvalArgs& a, cudaStream_t s) {
+  const int grid = eval_grid(a.n);
+  size_t smem = 0;
+  if (WANT_J) smem = (size_t)(EVAL_THREADS / 32) * 8 * (EvalRec<RIG>::SIZE * sizeof(double) + sizeof(int64_t));
+  auto k = evaluate_kernel<RIG, WANT_J>;
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    RCC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  k<<<grid, EVAL_THREADS, smem, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
 void launch_evaluate(bool rig, bool want_jac, const EvalArgs& a, cudaStream_t s) {
   if (a.n == 0) return;
-  const int grid = eval_grid(a.n);
   if (rig) {
-    if (want_jac) evaluate_kernel<true, true><<<grid, EVAL_THREADS, 0, s>>>(a);
-    else evaluate_kernel<true, false><<<grid, EVAL_THREADS, 0, s>>>(a);
+    if (want_jac) launch_evaluate_t<true, true>(a, s);
+    else launch_evaluate_t<true, false>(a, s);
   } else {
-    if (want_jac) evaluate_kernel<false, true><<<grid, EVAL_THREADS, 0, s>>>(a);
-    else evaluate_kernel<false, false><<<grid, EVAL_THREADS, 0, s>>>(a);
+    if (want_jac) launch_evaluate_t<false, true>(a, s);
+    else launch_evaluate_t<false, false>(a, s);
   }
-  RCC_CUDA(cudaGetLastError());
 }
 
 void launch_cost(bool rig, const EvalArgs& a, cudaStream_t s) {
