@@ -240,15 +240,35 @@ def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
     for v0 in range(0, n_views, chunk_views):
         v1 = min(n_views, v0 + chunk_views)
         nv = v1 - v0
+        Rv = rodrigues_np(views_t[v0:v1, 0:3])                                   # (nv,3,3)
+        # marker centres in the view/body frame: R^T (t_m - t_v)   (cheap conservative prefilter)
+        ctr = np.einsum('vji,vmj->vmi', Rv, markers_t[None, :, 3:6] - views_t[v0:v1, None, 3:6])
         for c in range(n_cam):
+            pc = ctr
+            if model == "rig":
+                Rx = rodrigues_np(ext_t[c, 0:3])
+                pc = (ctr - ext_t[c, 3:6]) @ Rx                                   # Rx^T (p - t_x)
+            zc = np.maximum(pc[..., 2], 1e-9)
+            margin = 0.35 * max(W, Himg) + intr_t[c, 0] * tag_size / zc          # distortion + tag extent
+            cand = ((pc[..., 2] > 0.05)
+                    & (np.abs(intr_t[c, 0] * pc[..., 0] / zc + intr_t[c, 2] - W / 2) < W / 2 + margin)
+                    & (np.abs(intr_t[c, 1] * pc[..., 1] / zc + intr_t[c, 3] - Himg / 2) < Himg / 2 + margin))
+            cv_, cm_ = np.nonzero(cand)
+            vv_c, mm_c = (cv_ + v0), cm_
+            uv_c, Z_c = project(model, np.broadcast_to(intr_t[c], (len(vv_c), 4)),
+                                np.broadcast_to(dist_t[c], (len(vv_c), 5)),
+                                np.broadcast_to(ext_t[c], (len(vv_c), 6)),
+                                views_t[vv_c], markers_t[mm_c], sizes[mm_c])
+            ok_c = ((Z_c > 0.1).all(-1) & (uv_c[..., 0] >= 0).all(-1) & (uv_c[..., 0] < W).all(-1)
+                    & (uv_c[..., 1] >= 0).all(-1) & (uv_c[..., 1] < Himg).all(-1))
+            # scatter back to the dense (view, marker) grid the thinning below works on
             vv = np.repeat(np.arange(v0, v1), n_markers)
             mm = np.tile(m_all, nv)
-            uv, Z = project(model, np.broadcast_to(intr_t[c], (len(vv), 4)),
-                            np.broadcast_to(dist_t[c], (len(vv), 5)),
-                            np.broadcast_to(ext_t[c], (len(vv), 6)),
-                            views_t[vv], markers_t[mm], sizes[mm])
-            ok = ((Z > 0.1).all(-1) & (uv[..., 0] >= 0).all(-1) & (uv[..., 0] < W).all(-1)
-                  & (uv[..., 1] >= 0).all(-1) & (uv[..., 1] < Himg).all(-1))
+            ok = np.zeros(nv * n_markers, bool)
+            flat = cv_ * n_markers + cm_
+            ok[flat[ok_c]] = True
+            uv = None
+            uv_lookup = (flat, uv_c)
             # thin to the requested visibility
             n_keep = int(round(visibility * n_markers))
             okm = ok.reshape(nv, n_markers)
@@ -264,7 +284,8 @@ def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
             vi_l.append(vv[sel].astype(dtype_idx))
             mi_l.append(mm[sel].astype(dtype_idx))
             ci_l.append(np.full(len(sel), c, dtype_idx))
-            px_l.append(uv[sel].reshape(-1, 8))
+            pos = np.searchsorted(uv_lookup[0], sel)          # flat is sorted (np.nonzero order)
+            px_l.append(uv_lookup[1][pos].reshape(-1, 8))
     view_idx = np.concatenate(vi_l)
     marker_idx = np.concatenate(mi_l)
     cam_idx = np.concatenate(ci_l)
