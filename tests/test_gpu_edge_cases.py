@@ -1,0 +1,163 @@
+"""GPU: edge cases of the domain -- empty / ragged inputs, unobserved blocks, duplicate
+observations, argument and call-order errors."""
+import numpy as np
+import pytest
+
+import ba_oracle as O
+from helpers import max_block_rel, oracle_blocks, oracle_reduced, rel_fro, to_oracle
+from robot_camera_calibration_b200 import _lib as L
+from robot_camera_calibration_b200.problem import BAProblem
+from robot_camera_calibration_b200.scenes import make_scene
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _keep(s, mask):
+    s.view_idx, s.marker_idx, s.cam_idx, s.pixels = s.view_idx[mask], s.marker_idx[mask], s.cam_idx[mask], s.pixels[mask]
+    return s
+
+
+def _check_against_oracle(s, elim="views"):
+    p = to_oracle(s)
+    ob = oracle_blocks(p, elim == "views")
+    S, b, *_ = oracle_reduced(p, elim == "views", 1e4)
+    with BAProblem.from_scene(s, eliminate=elim) as gp:
+        cost = gp.linearize()
+        nb = gp.normal_blocks()
+        gp.schur(1e4)
+        Sg, bg = gp.reduced_system()
+        gp.solve_step()
+        st = gp.step()
+    assert abs(cost - ob["cost"]) <= TOL * max(ob["cost"], 1e-300)
+    for k in ("Hee", "Hff", "W", "ge", "gf", "Hes", "Hfs"):
+        assert max_block_rel(nb[k], ob[k], floor=1e-6 * np.abs(ob[k]).max()) < TOL, k
+    assert rel_fro(Sg, S) < TOL and rel_fro(bg, b) < TOL
+    return st
+
+
+@pytest.mark.parametrize("elim", ["views", "markers"])
+def test_unobserved_view_and_marker_stay_put(elim):
+    s = make_scene(9, 12, 0.9, seed=51)
+    _keep(s, (s.view_idx != 4) & (s.marker_idx != 6))          # view 4 and tag 6 are never observed
+    st = _check_against_oracle(s, elim)
+    dv, dm = (st["d_e"], st["d_f"]) if elim == "views" else (st["d_f"], st["d_e"])
+    assert np.all(dv[4] == 0.0) and np.all(dm[6] == 0.0)
+    assert np.all(dm[0] == 0.0)                                 # gauge
+
+
+def test_ragged_segments_cross_every_chunk_boundary():
+    """views with 1, 5, 6, 7, 12, 13, 47, 48, 49, 97 ... tags: partial thread-groups, exact
+    multiples of the 6-block warp iteration, and segments split into several chunks."""
+    s = make_scene(130, 30, 1.0, seed=52, image_size=(2000, 1500))
+    want = sorted([1, 5, 6, 7, 12, 13, 47, 48, 49, 97, 61, 60, 120, 2], reverse=True)
+    counts = np.bincount(s.view_idx, minlength=len(s.views))
+    order = np.argsort(-counts)                       # views with the most visible tags first
+    keep = np.zeros(s.n_blocks, bool)
+    for v, n in zip(order, want):
+        idx = np.nonzero(s.view_idx == v)[0]
+        assert len(idx) >= n, (v, len(idx), n)
+        keep[idx[:n]] = True
+    _keep(s, keep)                                    # the other 16 views end up unobserved
+    got = np.bincount(s.view_idx, minlength=len(s.views))
+    assert sorted(got[got > 0].tolist(), reverse=True) == want
+    _check_against_oracle(s, "views")
+    _check_against_oracle(s, "markers")
+
+
+def test_duplicate_observations_are_summed():
+    """the same tag reported twice in one frame (and, in a rig, by two cameras)."""
+    s = make_scene(8, 10, 0.9, seed=53)
+    dup = np.arange(0, s.n_blocks, 5)
+    s.view_idx = np.concatenate([s.view_idx, s.view_idx[dup]])
+    s.marker_idx = np.concatenate([s.marker_idx, s.marker_idx[dup]])
+    s.cam_idx = np.concatenate([s.cam_idx, s.cam_idx[dup]])
+    s.pixels = np.concatenate([s.pixels, s.pixels[dup] + 0.5])
+    _check_against_oracle(s, "views")
+    r = make_scene(10, 8, 0.9, n_cam=3, model="rig", seed=54)      # overlapping cameras see the same tag
+    _check_against_oracle(r, "views")
+    _check_against_oracle(r, "markers")
+
+
+def test_single_observation_and_empty_problem():
+    s = make_scene(4, 3, 1.0, seed=55)
+    _keep(s, np.arange(s.n_blocks) == 0)
+    _check_against_oracle(s)
+    with BAProblem(3, 4, 1, 0) as gp:                              # no observations at all
+        gp.set_intrinsics(s.intr, s.dist)
+        gp.set_view_poses(s.views); gp.set_marker_poses(s.markers); gp.set_marker_sizes(s.sizes)
+        gp.set_observations(np.zeros(0, np.int32), np.zeros(0, np.int32), None, np.zeros((0, 8)))
+        assert gp.linearize() == 0.0
+        out = gp.evaluate()
+        assert out["cost"] == 0.0 and out["residuals"].shape == (0, 8)
+        nb = gp.normal_blocks()
+        assert not nb["Hee"].any() and not nb["Hss"].any()
+        summ = gp.solve(max_iterations=3)
+        assert summ["final_cost"] == 0.0
+        assert np.array_equal(gp.get_view_poses(), s.views)
+
+
+def test_argument_and_call_order_errors():
+    s = make_scene(5, 6, 0.9, seed=56)
+    with BAProblem(len(s.views), len(s.markers), 1, s.n_blocks) as gp:
+        with pytest.raises(L.RccError) as e:
+            gp.linearize()
+        assert e.value.status == L.RCC_NOT_READY
+        bad = s.view_idx.copy(); bad[3] = len(s.views)
+        with pytest.raises(L.RccError) as e:
+            gp.set_observations(bad, s.marker_idx, s.cam_idx, s.pixels)
+        assert e.value.status == L.RCC_BAD_ARG and "view index" in str(e.value)
+        bad = s.cam_idx.copy(); bad[0] = 1
+        with pytest.raises(L.RccError) as e:
+            gp.set_observations(s.view_idx, s.marker_idx, bad, s.pixels)
+        assert e.value.status == L.RCC_BAD_ARG
+        gp.set_observations(s.view_idx, s.marker_idx, s.cam_idx, s.pixels)
+        with pytest.raises(L.RccError) as e:
+            gp.schur(1e4)
+        assert e.value.status == L.RCC_NOT_READY
+        with pytest.raises(L.RccError) as e:
+            gp.set_constant("marker", 99)
+        assert e.value.status == L.RCC_BAD_ARG
+        with pytest.raises(L.RccError) as e:
+            gp.set_rig_extrinsics(np.zeros((1, 6)))
+        assert e.value.status == L.RCC_BAD_ARG
+        gp.set_intrinsics(s.intr, s.dist); gp.set_view_poses(s.views)
+        gp.set_marker_poses(s.markers); gp.set_marker_sizes(s.sizes)
+        gp.linearize()
+        with pytest.raises(L.RccError) as e:
+            gp.schur(-1.0)
+        assert e.value.status == L.RCC_BAD_ARG
+        with pytest.raises(L.RccError) as e:
+            gp.solve_step()
+        assert e.value.status == L.RCC_NOT_READY
+        with pytest.raises(L.RccError) as e:
+            gp.reduced_system()
+        assert e.value.status == L.RCC_NOT_READY
+
+
+def test_constant_intrinsics_and_all_views_constant():
+    s = make_scene(8, 9, 0.9, seed=57)
+    s.const_intr[:] = True
+    s.const_dist[:] = True
+    st = _check_against_oracle(s)
+    assert np.all(st["d_shared"] == 0.0)
+    s.const_views[:] = True                                     # only the tags move
+    p = to_oracle(s)
+    delta, *_ = O.lm_step(p, 1e4)
+    st = _check_against_oracle(s, "views")
+    assert np.all(st["d_e"] == 0.0)
+    o_view, o_marker, o_shared, n = p.offsets()
+    assert rel_fro(st["d_f"].ravel(), delta[o_marker:o_shared]) < 1e-6
+
+
+def test_deterministic_bitwise_repeatability():
+    s = make_scene(20, 40, 0.6, seed=58)
+    res = []
+    for _ in range(2):
+        with BAProblem.from_scene(s) as gp:
+            gp.linearize(); gp.schur(1e4)
+            S, b = gp.reduced_system()
+            nb = gp.normal_blocks()
+        res.append((S, b, nb["Hee"], nb["Hss"]))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)                             # fixed summation order, no atomics
