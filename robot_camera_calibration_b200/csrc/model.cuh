@@ -286,23 +286,6 @@ RCC_HD void eval_corner(const BlockGeom<RIG>& g, const double* __restrict__ sh, 
 // can store it (shared memory) immediately and keep register live ranges short.
 //   sink.shared(i, js[9], r)   sink.marker(i, jm[6])   sink.view(i, jv[6])   sink.ext(i, jx[6])
 // with i = 0 (u row), 1 (v row).  Returns the corner's depth.
-// residual of one corner only (Geo: BlockGeom<RIG> or any struct with the same member names)
-template <bool RIG, class Geo>
-RCC_HD void eval_corner_residual(const Geo& g, const double* __restrict__ sh, double ox, double oy, double pu,
-                                 double pv, double& r0, double& r1) {
-  double P[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) P[i] = g.Rcm[3 * i] * ox + g.Rcm[3 * i + 1] * oy + g.c0[i];
-  const double iz = 1.0 / P[2];
-  const double x = P[0] * iz, y = P[1] * iz;
-  const double xx = x * x, yy = y * y, xy = x * y;
-  const double r2 = xx + yy;
-  const double rad = 1.0 + sh[4] * r2 + sh[5] * (r2 * r2) + sh[8] * (r2 * r2 * r2);
-  const double tx = 2.0 * xy, ax = r2 + 2.0 * xx, ay = r2 + 2.0 * yy;
-  r0 = sh[0] * (x * rad + sh[6] * tx + sh[7] * ax) + sh[2] - pu;
-  r1 = sh[1] * (y * rad + sh[6] * ay + sh[7] * tx) + sh[3] - pv;
-}
-
 template <bool RIG, class Geo, class Sink>
 RCC_HD double eval_corner_emit(const Geo& g, const double* __restrict__ sh, double ox, double oy,
                                double pu, double pv, Sink& sink, double& r0, double& r1) {
