@@ -4,7 +4,9 @@
 //
 // One thread per tag corner (4 threads = one observation block); each thread
 // writes its two residual rows of every Jacobian block as 16-byte vector
-// stores.  The kernel is HBM-write-bound: 1 408 B out per 72 B in.
+// stores.  The kernel is HBM-write-bound: 1 408 B out per 72 B in.  Rows are staged in shared
+// memory in the Ceres layout and leave the SM as TMA bulk copies (cp.async.bulk, one per
+// (tag, Jacobian block) record).
 #include "common.cuh"
 #include "kernels.h"
 #include "model.cuh"
@@ -35,17 +37,11 @@ struct EvalRec {
   static constexpr int SIZE = RIG ? 226 : 178;   // +2: consecutive records shift by 16 B across the smem banks
 };
 
-// cooperative, coalesced copy-out of one output array for the 8 blocks of a warp:
-// K doubles per block, contiguous in global memory per block (caller order via orig)
-template <int K, int REC>
-__device__ __forceinline__ void copy_out(double* __restrict__ dst, const double* wrec, int off, const int64_t* o8,
-                                         int nblk, int lane) {
-  constexpr int PIECES = K / 2;  // 16-byte pieces per block
-  for (int idx = lane; idx < nblk * PIECES; idx += 32) {
-    const int q = idx / PIECES, pc = idx - q * PIECES;
-    const double2 v = *reinterpret_cast<const double2*>(wrec + q * REC + off + 2 * pc);
-    *reinterpret_cast<double2*>(dst + o8[q] * K + 2 * pc) = v;
-  }
+// TMA bulk copy shared::cta -> global (16-byte aligned, size a multiple of 16); SASS: UBLKCP
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
 }
 
 template <bool RIG, bool WANT_J>
@@ -63,11 +59,30 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a
   if (g < a.n) {
     const int vi = a.view_idx[g], mi = a.marker_idx[g], cam = a.cam[g];
     constexpr int SP = RIG ? 15 : 9;
+    // expanded pose records as 16-byte loads (the 4 corner lanes of a tag read the same lines)
+    double vx[POSEX], mx[POSEX], xx[POSEX];
+    {
+      const double2* pv = reinterpret_cast<const double2*>(a.view_x + (size_t)vi * POSEX);
+      const double2* pm = reinterpret_cast<const double2*>(a.marker_x + (size_t)mi * POSEX);
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const double2 u = pv[k], w = pm[k];
+        vx[2 * k] = u.x; vx[2 * k + 1] = u.y;
+        mx[2 * k] = w.x; mx[2 * k + 1] = w.y;
+      }
+      if (RIG) {
+        const double2* pe = reinterpret_cast<const double2*>(a.ext_x + (size_t)cam * POSEX);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          const double2 u = pe[k];
+          xx[2 * k] = u.x; xx[2 * k + 1] = u.y;
+        }
+      }
+    }
     BlockGeom<RIG> geo;
-    block_geometry<RIG>(a.view_x + (size_t)vi * POSEX, a.marker_x + (size_t)mi * POSEX,
-                        RIG ? a.ext_x + (size_t)cam * POSEX : nullptr, geo);
+    block_geometry<RIG>(vx, mx, RIG ? xx : nullptr, geo);
     double ox, oy;
-    corner_xy(t, 0.5 * a.sizes[mi], ox, oy);
+    corner_xy(t, mx[PX_HS], ox, oy);
     const double2 px = *reinterpret_cast<const double2*>(a.pix + g * 8 + 2 * t);
     CornerRows<RIG> c;
     eval_corner<RIG, WANT_J>(geo, a.shared + (size_t)cam * SP, ox, oy, px.x, px.y, c);
@@ -112,18 +127,29 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a
     }
   }
   if (WANT_J) {
+    // hand the copy-out to the TMA engine: one bulk copy (shared -> global) per (block, array)
+    // record, 64..384 contiguous bytes each, issued by one lane per record
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the async proxy
     __syncwarp();
-    // blocks of this warp: g0 .. g0+7 (clipped)
     const int64_t g0 = ((int64_t)blockIdx.x * EVAL_THREADS + warp * 32) >> 2;
     const int nblk = (int)max((int64_t)0, min((int64_t)8, a.n - g0));
-    if (nblk > 0) {
-      if (a.residuals) copy_out<8, ER::SIZE>(a.residuals, wrec, ER::RES, wpos, nblk, lane);
-      if (a.jac_intr) copy_out<32, ER::SIZE>(a.jac_intr, wrec, ER::JI, wpos, nblk, lane);
-      if (a.jac_dist) copy_out<40, ER::SIZE>(a.jac_dist, wrec, ER::JD, wpos, nblk, lane);
-      if (a.jac_view) copy_out<48, ER::SIZE>(a.jac_view, wrec, ER::JV, wpos, nblk, lane);
-      if (a.jac_marker) copy_out<48, ER::SIZE>(a.jac_marker, wrec, ER::JM, wpos, nblk, lane);
-      if (RIG && a.jac_ext) copy_out<48, ER::SIZE>(a.jac_ext, wrec, ER::JX, wpos, nblk, lane);
+    constexpr int NARR = RIG ? 6 : 5;
+    for (int idx = lane; idx < nblk * NARR; idx += 32) {
+      const int q = idx / NARR, arr = idx - q * NARR;
+      double* dst = nullptr;
+      int off = 0, k = 0;
+      switch (arr) {
+        case 0: dst = a.residuals; off = ER::RES; k = 8; break;
+        case 1: dst = a.jac_intr; off = ER::JI; k = 32; break;
+        case 2: dst = a.jac_dist; off = ER::JD; k = 40; break;
+        case 3: dst = a.jac_view; off = ER::JV; k = 48; break;
+        case 4: dst = a.jac_marker; off = ER::JM; k = 48; break;
+        default: dst = a.jac_ext; off = ER::JX; k = 48; break;
+      }
+      if (dst) bulk_store(dst + wpos[q] * k, wrec + q * ER::SIZE + off, k * (int)sizeof(double));
     }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
   }
   if (a.loss != 0) {
     // the 4 corner threads of a tag are adjacent lanes: rho(sum of the 8 squared residuals) / 4 each
