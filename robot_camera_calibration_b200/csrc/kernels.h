@@ -185,14 +185,16 @@ void launch_schur_prep(const SchurPrepArgs& a, cudaStream_t s);
 struct SchurSyrkArgs {
   int32_t n_f, n_e;
   int32_t n_shared, n_bb;
-  int32_t tile_w;                // kept blocks per column tile
-  int32_t n_tiles;               // ceil(n_f / tile_w)
+  int32_t tile_w;                // kept blocks per column sub-tile of tile_ptr (32)
+  int32_t n_tiles;               // ceil(n_f / tile_w) sub-tiles
   int32_t ld;                    // row stride of S
   const int32_t* col_ptr;        // [n_f+1]
   const int32_t* col_pair;       // pair ids of column f, ascending e
   const int32_t* pair_e;         // [n_pairs]
   const int32_t* pair_f;         // [n_pairs]
   const int32_t* tile_ptr;       // [n_e*(n_tiles+1)]
+  const int32_t* cta_list;       // [n_ctas][2] (f, column tile) of schur_syrk_kernel, heaviest first
+  int32_t n_ctas;
   const double* Y;
   const double* Yb;
   const double* Hff;             // [n_f*36]
@@ -200,7 +202,9 @@ struct SchurSyrkArgs {
   const double* Hfs;             // [n_f*6*n_shared]
   double* S;                     // [(n + extra rows) * ld]
 };
-void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s);
+void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s);     // kept x kept blocks (upper triangle)
+void launch_schur_border(const SchurSyrkArgs& a, cudaStream_t s);   // kept x [shared | rhs] strip
+int schur_cta_subtiles();        // tile_ptr sub-tiles covered by one schur_syrk CTA column tile
 
 struct SchurSharedArgs {
   int32_t n_e, n_f, n_shared, n_bb, ld;

@@ -89,6 +89,9 @@ rcc_ba_problem::~rcc_ba_problem() {
   if (solver) cusolverDnDestroy(solver);
   if (h_pinned) cudaFreeHost(h_pinned);
   if (own_stream && stream) cudaStreamDestroy(stream);
+  if (side_stream) cudaStreamDestroy(side_stream);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
 }
 
 typedef rcc_ba_problem P_t;
@@ -284,8 +287,8 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
   P->pair_members.upload(members, s);
 
   // ---- column structure (pairs of kept block f, ascending e)
+  std::vector<int32_t> col_ptr((size_t)P->n_f + 1, 0), col_pair((size_t)P->n_pairs);
   {
-    std::vector<int32_t> col_ptr((size_t)P->n_f + 1, 0), col_pair((size_t)P->n_pairs);
     for (int64_t p = 0; p < P->n_pairs; ++p) col_ptr[pair_f[p] + 1]++;
     for (int f = 0; f < P->n_f; ++f) col_ptr[f + 1] += col_ptr[f];
     std::vector<int32_t> cur(col_ptr.begin(), col_ptr.end() - 1);
@@ -294,8 +297,8 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
     P->col_pair.upload(col_pair, s);
     RCC_CUDA(cudaStreamSynchronize(s));
   }
-  // ---- column tiles of the Schur SYRK
-  P->tile_w = std::max(1, std::min(env_int("RCC_TILE_W", 128), P->n_f));
+  // ---- 32-block column sub-tiles of the Schur SYRK: tile_ptr[e][J] = first pair of row e with f >= 32 J
+  P->tile_w = 32;
   P->n_tiles = (P->n_f + P->tile_w - 1) / P->tile_w;
   {
     const int nt = P->n_tiles;
@@ -311,6 +314,22 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
       }
     }
     P->tile_ptr.upload(tile_ptr, s);
+    // work list of the SYRK: one CTA per (block row f, column tile J on or right of the diagonal),
+    // column tile major so that co-resident CTAs read the same columns of Y (L2 locality; a
+    // heaviest-first order was measured slower on cfg4 for that reason)
+    const int cs = schur_cta_subtiles();
+    const int nct = (nt + cs - 1) / cs;
+    std::vector<int64_t> order;
+    for (int J = 0; J < nct; ++J)
+      for (int f = 0; f < std::min(P->n_f, (J + 1) * 32 * cs); ++f) order.push_back((int64_t)f * nct + J);
+    std::vector<int32_t> cta_list(2 * order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+      cta_list[2 * i] = (int32_t)(order[i] / nct);
+      cta_list[2 * i + 1] = (int32_t)(order[i] % nct);
+    }
+    P->n_syrk_ctas = (int)order.size();
+    if (cta_list.empty()) cta_list.assign(2, 0);
+    P->syrk_ctas.upload(cta_list, s);
     RCC_CUDA(cudaStreamSynchronize(s));
   }
 
@@ -423,23 +442,28 @@ static void do_schur(P_t* P, double radius) {
     launch_schur_prep(a, P->stream);
   }
   {
-    Scoped t(P, ST_SCHUR_SYRK, 1);
+    // the border strip, the shared x shared corner and the tail rows depend only on schur_prep:
+    // they run on the side stream beside the block-sparse SYRK and join before the stage ends
+    Scoped t(P, ST_SCHUR_SYRK, 5);
     SchurSyrkArgs a{};
     a.n_f = P->n_f; a.n_e = P->n_e; a.n_shared = P->n_shared; a.n_bb = P->n_bb;
     a.tile_w = P->tile_w; a.n_tiles = P->n_tiles; a.ld = P->ld;
     a.col_ptr = P->col_ptr.p; a.col_pair = P->col_pair.p; a.pair_e = P->pair_e.p; a.pair_f = P->pair_f.p;
+    a.cta_list = P->syrk_ctas.p; a.n_ctas = P->n_syrk_ctas;
     a.tile_ptr = P->tile_ptr.p; a.Y = P->Y.p; a.Yb = P->Yb.p; a.Hff = P->Hff.p; a.gf = P->gf.p; a.Hfs = P->Hfs.p;
     a.S = P->S.p;
-    launch_schur_syrk(a, P->stream);
-  }
-  {
-    Scoped t(P, ST_SCHUR_SHARED, 3);
-    SchurSharedArgs a{P->n_e, P->n_f, P->n_shared, P->n_bb, P->ld, P->Yb.p, P->Hss.p, P->gs.p, P->shared_scratch.p,
-                      P->S.p};
-    launch_schur_shared(a, P->stream);
+    RCC_CUDA(cudaEventRecord(P->ev_fork, P->stream));
+    RCC_CUDA(cudaStreamWaitEvent(P->side_stream, P->ev_fork, 0));
+    launch_schur_border(a, P->side_stream);
+    SchurSharedArgs sh{P->n_e, P->n_f, P->n_shared, P->n_bb, P->ld, P->Yb.p, P->Hss.p, P->gs.p, P->shared_scratch.p,
+                       P->S.p};
+    launch_schur_shared(sh, P->side_stream);
     ReducedTailArgs r{P->n_f, P->n_shared, P->ld, P->Hff.p, P->gf.p, P->Hss.p, P->gs.p, P->cost2_cam.p, P->n_cam,
                       P->S.p};
-    launch_reduced_tail(r, P->stream);
+    launch_reduced_tail(r, P->side_stream);
+    RCC_CUDA(cudaEventRecord(P->ev_join, P->side_stream));
+    launch_schur_syrk(a, P->stream);
+    RCC_CUDA(cudaStreamWaitEvent(P->stream, P->ev_join, 0));
   }
   P->schur_done = true;
   P->step_ready = P->cand_ready = false;
@@ -765,6 +789,9 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     RCC_REQUIRE((int64_t)P->n_red * P->ld < (int64_t)1 << 40, RCC_BAD_ARG, "reduced system too large");
     RCC_CUDA(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     P->own_stream = true;
+    RCC_CUDA(cudaStreamCreateWithFlags(&P->side_stream, cudaStreamNonBlocking));
+    RCC_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+    RCC_CUDA(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
     RCC_CUDA(cudaMallocHost(&P->h_pinned, 64 * sizeof(double)));
     cudaStream_t s = P->stream;
     P->views.alloc((size_t)P->n_views * 6); P->views.zero(s);

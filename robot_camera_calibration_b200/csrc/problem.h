@@ -44,10 +44,13 @@ struct rcc_ba_problem {
   int n_views = 0, n_markers = 0, n_e = 0, n_f = 0;
   int n_bb = 2, n_red = 0, ld = 0;
   int64_t n_obs = 0, n_pairs = 0;
-  int tile_w = 128, n_tiles = 1;
+  int tile_w = 32, n_tiles = 1, n_syrk_ctas = 0;
   int n_chunks_e = 0, n_chunks_f = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // fork/join side stream: small kernels that only depend on the previous stage run beside the big one
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   int64_t launch_count = 0;
 
@@ -63,7 +66,7 @@ struct rcc_ba_problem {
   rcc::DBuf<double> e_pix, f_pix, pix_staging;
   rcc::DBuf<rcc::Chunk> e_chunks, f_chunks;
   rcc::DBuf<int32_t> cam_chunks_e, cam_ptr_e, cam_chunks_f, cam_ptr_f;
-  rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, col_ptr, col_pair, tile_ptr, e_count;
+  rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, col_ptr, col_pair, tile_ptr, syrk_ctas, e_count;
   rcc::DBuf<uint8_t> e_const;
 
   // linearisation products

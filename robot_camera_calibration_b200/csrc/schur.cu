@@ -138,112 +138,304 @@ void launch_schur_prep(const SchurPrepArgs& a, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------
-// schur_syrk: CTA (f, J) owns the 6 x (6*tile_w) strip of S in block row f and
-// column tile J (J == n_tiles: the shared/rhs border).  It walks the pairs
-// (e, f) of column f; for each, every thread takes one column of one partner
-// block Y_ef' of row e and accumulates  Y_ef^T Y_ef'[:,c]  into the strip held
-// in shared memory.
+// schur_syrk (v2): CTA (f, J) owns the 6 x (6 * SY_WARPS * 32) strip of S in
+// block row f and column tile J; warp w of the CTA owns the 32 kept blocks of
+// sub-tile J * SY_WARPS + w and keeps their 6 x 6 output blocks in its private
+// slice of shared memory.  The CTA walks the pairs (e, f) of column f in
+// batches (Y_ef staged by cp.async, double buffered, one barrier per batch);
+// for each pair every warp holds Y_ef in 36 registers and its lanes take the
+// (partner block f', column c) items of row e that fall in the warp's sub-tile:
+// 48 B coalesced load of Y_ef'[:, c], 36 DFMA, 6-double read-modify-write on the
+// warp's slice.  No barrier per pair, no cross-warp traffic, fixed summation
+// order (ascending e) -> bitwise reproducible.
 // ---------------------------------------------------------------------------
-constexpr int SYRK_THREADS = 384;
-constexpr int SYRK_BATCH = 32;
+#ifndef RCC_SY_WARPS
+#define RCC_SY_WARPS 2
+#endif
+#ifndef RCC_SY_SUB
+#define RCC_SY_SUB 32
+#endif
+#ifndef RCC_SY_CTAS
+#define RCC_SY_CTAS 6
+#endif
+constexpr int SY_WARPS = RCC_SY_WARPS;
+constexpr int SY_SUB = RCC_SY_SUB;   // kept blocks per warp sub-tile: a multiple of SchurSyrkArgs::tile_w (32)
+constexpr int SY_G = SY_SUB / 32;    // tile_ptr entries per warp sub-tile
+constexpr int SY_BATCH = 32;         // pairs of column f staged per round
+static_assert(SY_SUB % 32 == 0, "warp sub-tile must be a multiple of the tile_ptr granularity");
+int schur_cta_subtiles() { return SY_WARPS * SY_G; }
 
-__global__ void __launch_bounds__(SYRK_THREADS) schur_syrk_kernel(const SchurSyrkArgs a) {
-  extern __shared__ double sm[];
-  const int f = blockIdx.x;
-  const int J = blockIdx.y;
-  const int tile_of_f = f / a.tile_w;
-  if (J < tile_of_f) return;
-  const bool border = (J == a.n_tiles);
-  const int width = border ? a.n_bb * 6 : 6 * min(a.tile_w, a.n_f - J * a.tile_w);  // strip columns
-  const int wpad = width | 1;  // odd row stride (in doubles) to spread the 6 rows over banks
-  double* acc = sm;                       // [6][wpad]
-  double* yi = sm + 6 * wpad;             // [SYRK_BATCH][36]  staged Y_ef of the current batch
-  int* meta = reinterpret_cast<int*>(yi + SYRK_BATCH * 36);  // [SYRK_BATCH][2] partner range
-  const int tid = threadIdx.x;
-  for (int k = tid; k < 6 * wpad; k += SYRK_THREADS) acc[k] = 0.0;
+__device__ __forceinline__ void sy_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 
+// position of a warp in the (pair, step) sequence of a staged batch -- warp-uniform
+struct SyCursor { int q, lo, n_items, base; };
+// moves to the next 32-item step; lane q of the warp holds the partner range [lo_q, hi_q) of pair q
+__device__ __forceinline__ bool sy_advance(SyCursor& c, int nb, int lo_lane, int hi_lane) {
+  c.base += 32;
+  while (c.base >= c.n_items) {
+    if (++c.q >= nb) return false;
+    c.lo = __shfl_sync(0xffffffffu, lo_lane, c.q);
+    c.n_items = (__shfl_sync(0xffffffffu, hi_lane, c.q) - c.lo) * 6;
+    c.base = 0;
+  }
+  return true;
+}
+// one lane's item of a step: column c of partner block Y_ef' and its slot in the warp's output slice
+struct SyItem { double2 y0, y1, y2; int pf, col; };   // pf < 0: idle lane.  (raw loads only: nothing here waits on memory)
+__device__ __forceinline__ void sy_load(const SchurSyrkArgs& a, const SyCursor& c, int lane, int subbase, SyItem& it) {
+  const int idx = c.base + lane;
+  it.pf = -1;
+  it.col = 0;
+  if (idx < c.n_items) {
+    const int jj = idx / 6, col = idx - jj * 6;
+    const int j = c.lo + jj;
+    const double2* yp = reinterpret_cast<const double2*>(a.Y + (size_t)j * 36 + col * 6);
+    it.y0 = yp[0];
+    it.y1 = yp[1];
+    it.y2 = yp[2];
+    it.pf = a.pair_f[j];
+    it.col = col;
+  }
+}
+
+__global__ void __launch_bounds__(SY_WARPS * 32, RCC_SY_CTAS) schur_syrk_kernel(const SchurSyrkArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  // work list: (block row f, column tile J >= tile of f), largest estimated work first
+  const int f = a.cta_list[2 * blockIdx.x];
+  const int J = a.cta_list[2 * blockIdx.x + 1];
+  const int sub_of_f = f / SY_SUB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double* acc = sm + warp * (SY_SUB * 36);            // [SY_SUB blocks][6 columns][6 rows]
+  double* yi = sm + SY_WARPS * SY_SUB * 36;           // [2][SY_BATCH][36] staged Y_ef
+  for (int k = lane; k < SY_SUB * 36; k += 32) acc[k] = 0.0;
+
+  const int js = J * SY_WARPS + warp;                 // this warp's sub-tile
+  const bool active = (js >= sub_of_f) && (js * SY_G < a.n_tiles);
+  const int subbase = js * SY_SUB;
   const int c0 = a.col_ptr[f], c1 = a.col_ptr[f + 1];
-  const int colbase = J * a.tile_w;  // first kept block of this tile
-  for (int cb = c0; cb < c1; cb += SYRK_BATCH) {
-    const int nb = min(SYRK_BATCH, c1 - cb);
-    __syncthreads();
-    // stage metadata + Y_ef blocks of the batch
-    if (tid < nb) {
-      const int p = a.col_pair[cb + tid];
-      const int e = a.pair_e[p];
-      int lo, hi;
-      if (border) {
-        lo = e * a.n_bb;
-        hi = lo + a.n_bb;
-      } else {
-        const int* tp = a.tile_ptr + (size_t)e * (a.n_tiles + 1);
-        lo = (J == tile_of_f) ? p : tp[J];
-        hi = tp[J + 1];
-      }
-      meta[2 * tid] = lo;
-      meta[2 * tid + 1] = hi;
+  const int tps = a.n_tiles + 1;
+
+  auto stage = [&](int cb, int buf) {
+    const int nb = min(SY_BATCH, c1 - cb);
+    double2* dst = reinterpret_cast<double2*>(yi + buf * SY_BATCH * 36);
+    for (int k = tid; k < nb * 18; k += SY_WARPS * 32) {
+      const int q = k / 18, piece = k - q * 18;
+      const int p = a.col_pair[cb + q];
+      sy_cp_async16(dst + k, reinterpret_cast<const double2*>(a.Y + (size_t)p * 36) + piece);
     }
-    for (int k = tid; k < nb * 36; k += SYRK_THREADS) {
-      const int q = k / 36;
-      yi[k] = a.Y[(size_t)a.col_pair[cb + q] * 36 + (k - q * 36)];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // lane q of every warp: partner range of pair q of the batch inside the warp's sub-tile
+  auto meta = [&](int cb, int& lo, int& hi) {
+    lo = 0;
+    hi = 0;
+    if (active && cb + lane < c1) {
+      const int p = a.col_pair[cb + lane];
+      const int* tp = a.tile_ptr + (size_t)a.pair_e[p] * tps;
+      lo = (js == sub_of_f) ? p : tp[js * SY_G];
+      hi = tp[min((js + 1) * SY_G, a.n_tiles)];
     }
-    __syncthreads();
-    const double* src = border ? a.Yb : a.Y;
-    for (int q = 0; q < nb; ++q) {
-      const int lo = meta[2 * q], hi = meta[2 * q + 1];
-      const double* Yi = yi + q * 36;  // column-major: Yi[r*6+k] = Y[k][r]
-      for (int idx = tid; idx < (hi - lo) * 6; idx += SYRK_THREADS) {
-        const int j = lo + idx / 6, c = idx % 6;
-        const double2* yp = reinterpret_cast<const double2*>(src + (size_t)j * 36 + c * 6);
-        const double2 y0 = yp[0], y1 = yp[1], y2 = yp[2];
-        const int col = border ? (j - lo) * 6 + c : (a.pair_f[j] - colbase) * 6 + c;
+  };
+
+  int lo_cur, hi_cur, lo_nxt = 0, hi_nxt = 0;
+  if (c0 < c1) stage(c0, 0);
+  meta(c0, lo_cur, hi_cur);
+  int buf = 0;
+  for (int cb = c0; cb < c1; cb += SY_BATCH, buf ^= 1) {
+    const int nb = min(SY_BATCH, c1 - cb);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // batch `cb` staged by everyone; batch `cb - SY_BATCH` consumed by everyone
+    if (cb + SY_BATCH < c1) {
+      stage(cb + SY_BATCH, buf ^ 1);
+      meta(cb + SY_BATCH, lo_nxt, hi_nxt);
+    }
+    if (active) {
+      const double* ybuf = yi + buf * SY_BATCH * 36;
+      // The warp walks the (pair, 32-item step) sequence of the batch; the global loads of step s+1
+      // (partner column, partner index) are issued before the arithmetic of step s.
+      SyCursor cur{-1, 0, 0, 0}, nxt;
+      SyItem it_c, it_n;
+      bool have = sy_advance(cur, nb, lo_cur, hi_cur);
+      if (have) sy_load(a, cur, lane, subbase, it_c);
+      int q_loaded = -1;
+      double Yi[36];   // Y_ef, column-major: Yi[r * 6 + k] = Y_ef[k][r]
+      while (have) {
+        nxt = cur;
+        const bool have_n = sy_advance(nxt, nb, lo_cur, hi_cur);
+        if (have_n) sy_load(a, nxt, lane, subbase, it_n);
+        if (cur.q != q_loaded) {
+          const double2* src = reinterpret_cast<const double2*>(ybuf + cur.q * 36);
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double* yr = Yi + r * 6;
-          double v = yr[0] * y0.x;
-          v = fma(yr[1], y0.y, v);
-          v = fma(yr[2], y1.x, v);
-          v = fma(yr[3], y1.y, v);
-          v = fma(yr[4], y2.x, v);
-          v = fma(yr[5], y2.y, v);
-          acc[r * wpad + col] += v;
+          for (int i = 0; i < 18; ++i) {
+            const double2 v = src[i];
+            Yi[2 * i] = v.x;
+            Yi[2 * i + 1] = v.y;
+          }
+          q_loaded = cur.q;
         }
+        if (it_c.pf >= 0) {
+          double v[6];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            double t = Yi[r * 6] * it_c.y0.x;
+            t = fma(Yi[r * 6 + 1], it_c.y0.y, t);
+            t = fma(Yi[r * 6 + 2], it_c.y1.x, t);
+            t = fma(Yi[r * 6 + 3], it_c.y1.y, t);
+            t = fma(Yi[r * 6 + 4], it_c.y2.x, t);
+            t = fma(Yi[r * 6 + 5], it_c.y2.y, t);
+            v[r] = t;
+          }
+          double2* ap = reinterpret_cast<double2*>(acc + (it_c.pf - subbase) * 36 + it_c.col * 6);
+          double2 a0 = ap[0], a1 = ap[1], a2 = ap[2];
+          a0.x += v[0]; a0.y += v[1];
+          a1.x += v[2]; a1.y += v[3];
+          a2.x += v[4]; a2.y += v[5];
+          ap[0] = a0; ap[1] = a1; ap[2] = a2;
+        }
+        __syncwarp();   // the next pair may touch the same output columns from other lanes
+        cur = nxt;
+        it_c = it_n;
+        have = have_n;
       }
-      __syncthreads();
+    }
+    lo_cur = lo_nxt;
+    hi_cur = hi_nxt;
+  }
+  // S strip = base - acc   (upper triangle in block granularity), rows written as contiguous runs
+  if (!active) return;
+  __syncwarp();
+  const int nblk = min(SY_SUB, a.n_f - subbase);
+  const size_t row0 = (size_t)6 * f;
+  for (int r = 0; r < 6; ++r) {
+    for (int cl = lane; cl < nblk * 6; cl += 32) {
+      const int fl = cl / 6, c = cl - fl * 6;
+      const int fp = subbase + fl;
+      if (fp < f) continue;
+      double base = 0.0;
+      if (fp == f) base = a.Hff[(size_t)f * 36 + r * 6 + c];
+      a.S[(row0 + r) * a.ld + (size_t)6 * subbase + cl] = base - acc[fl * 36 + c * 6 + r];
     }
   }
-  __syncthreads();
-  // S strip = base - acc   (upper triangle in block granularity)
-  const size_t row0 = (size_t)6 * f;
-  for (int k = tid; k < 6 * width; k += SYRK_THREADS) {
-    const int r = k / width, cl = k - r * width;
-    double base = 0.0;
-    int gc;
-    if (border) {
-      gc = 6 * a.n_f + cl;
-      if (gc >= a.ld) continue;
-      if (cl < a.n_shared) base = a.Hfs[((size_t)f * 6 + r) * a.n_shared + cl];
-      else if (cl == a.n_shared) base = a.gf[(size_t)f * 6 + r];
-    } else {
-      gc = 6 * colbase + cl;
-      if (gc < 6 * f) continue;
-      if (gc < 6 * f + 6) base = a.Hff[(size_t)f * 36 + r * 6 + (gc - 6 * f)];
+}
+
+// border strip of block row f:  [H_fs | g_f] - sum_e Y_ef^T Yb_e.  Every pair of column f meets every
+// border block, so a lane owns fixed border columns and keeps their 6-row outputs in registers:
+// lane = (slot u, column); the (warp, slot) slices stride over the staged pairs and are summed in a
+// fixed order at the end.  Y_ef and e are staged per batch exactly as in schur_syrk_kernel.
+constexpr int SB_WARPS = 4;
+constexpr int SB_MAXPASS = 4;   // up to 128 border columns (n_shared <= 125)
+__global__ void __launch_bounds__(SB_WARPS * 32) schur_border_kernel(const SchurSyrkArgs a) {
+  __shared__ __align__(16) double yi[2][SY_BATCH * 36];
+  __shared__ int se[2][SY_BATCH];
+  __shared__ double red[SB_WARPS * 32 * 6];
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncol = a.n_bb * 6;
+  const int cw = min(32, ncol);          // columns per pass
+  const int U = 32 / cw;                 // pair slots per warp
+  const int npass = (ncol + 31) / 32;
+  const int u = lane / cw, cl = lane - u * cw;
+  const bool lane_on = u < U;
+  const int c0 = a.col_ptr[f], c1 = a.col_ptr[f + 1];
+  double acc[SB_MAXPASS][6];
+#pragma unroll
+  for (int ps = 0; ps < SB_MAXPASS; ++ps)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) acc[ps][r] = 0.0;
+
+  auto stage = [&](int cb, int buf) {
+    const int nb = min(SY_BATCH, c1 - cb);
+    double2* dst = reinterpret_cast<double2*>(yi[buf]);
+    for (int k = tid; k < nb * 18; k += SB_WARPS * 32) {
+      const int q = k / 18, piece = k - q * 18;
+      const int p = a.col_pair[cb + q];
+      sy_cp_async16(dst + k, reinterpret_cast<const double2*>(a.Y + (size_t)p * 36) + piece);
     }
-    a.S[(row0 + r) * a.ld + gc] = base - acc[r * wpad + cl];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid < nb) se[buf][tid] = a.pair_e[a.col_pair[cb + tid]];
+  };
+  if (c0 < c1) stage(c0, 0);
+  int buf = 0;
+  for (int cb = c0; cb < c1; cb += SY_BATCH, buf ^= 1) {
+    const int nb = min(SY_BATCH, c1 - cb);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (cb + SY_BATCH < c1) stage(cb + SY_BATCH, buf ^ 1);
+    if (lane_on) {
+#pragma unroll 2
+      for (int q = warp * U + u; q < nb; q += SB_WARPS * U) {
+        const int e = se[buf][q];
+        const double2* Yi = reinterpret_cast<const double2*>(yi[buf] + q * 36);
+#pragma unroll
+        for (int ps = 0; ps < SB_MAXPASS; ++ps) {
+          const int col = ps * 32 + cl;
+          if (ps < npass && col < ncol) {
+            const double2* yp =
+                reinterpret_cast<const double2*>(a.Yb + ((size_t)e * a.n_bb + col / 6) * 36 + (col % 6) * 6);
+            const double2 y0 = yp[0], y1 = yp[1], y2 = yp[2];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              const double2 u0 = Yi[3 * r], u1 = Yi[3 * r + 1], u2 = Yi[3 * r + 2];
+              double t = u0.x * y0.x;
+              t = fma(u0.y, y0.y, t);
+              t = fma(u1.x, y1.x, t);
+              t = fma(u1.y, y1.y, t);
+              t = fma(u2.x, y2.x, t);
+              t = fma(u2.y, y2.y, t);
+              acc[ps][r] += t;
+            }
+          }
+        }
+      }
+    }
+  }
+  // fixed-order sum over the (warp, slot) slices
+#pragma unroll
+  for (int ps = 0; ps < SB_MAXPASS; ++ps) {
+    if (ps >= npass) break;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 6; ++r) red[tid * 6 + r] = acc[ps][r];
+    __syncthreads();
+    const int col = ps * 32 + tid;
+    if (tid < cw && col < ncol) {
+      const int gc = 6 * a.n_f + col;
+      if (gc < a.ld) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double sum = 0.0;
+          for (int w = 0; w < SB_WARPS; ++w)
+            for (int uu = 0; uu < U; ++uu) sum += red[(w * 32 + uu * cw + tid) * 6 + r];
+          double base = 0.0;
+          if (col < a.n_shared) base = a.Hfs[((size_t)f * 6 + r) * a.n_shared + col];
+          else if (col == a.n_shared) base = a.gf[(size_t)f * 6 + r];
+          a.S[((size_t)6 * f + r) * a.ld + gc] = base - sum;
+        }
+      }
+    }
   }
 }
 
 void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s) {
   if (a.n_f == 0) return;
-  const int wmax = max(a.tile_w * 6, a.n_bb * 6) | 1;
-  const size_t smem = (size_t)(6 * wmax + SYRK_BATCH * 36) * sizeof(double) + SYRK_BATCH * 2 * sizeof(int);
-  static size_t attr = 0;
-  if (smem > attr) {
+  RCC_REQUIRE(a.tile_w == 32, RCC_BAD_ARG, "schur_syrk: tile_ptr granularity must be 32");
+  const size_t smem = (size_t)(SY_WARPS * SY_SUB * 36 + 2 * SY_BATCH * 36) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
     RCC_CUDA(cudaFuncSetAttribute(schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr = true;
   }
-  dim3 grid(a.n_f, a.n_tiles + 1);
-  schur_syrk_kernel<<<grid, SYRK_THREADS, smem, s>>>(a);
+  if (a.n_ctas > 0) schur_syrk_kernel<<<a.n_ctas, SY_WARPS * 32, smem, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
+void launch_schur_border(const SchurSyrkArgs& a, cudaStream_t s) {
+  if (a.n_f == 0) return;
+  RCC_REQUIRE(a.n_bb * 6 <= 32 * SB_MAXPASS, RCC_BAD_ARG, "schur_border: more than 128 border columns");
+  schur_border_kernel<<<a.n_f, SB_WARPS * 32, 0, s>>>(a);
   RCC_CUDA(cudaGetLastError());
 }
 
