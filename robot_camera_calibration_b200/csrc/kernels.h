@@ -8,53 +8,39 @@
 namespace rcc {
 
 // ---------------------------------------------------------------------------
-// Tile-pass geometry of the fused linearise+assemble kernel (K2).
+// Geometry of the fused linearise+assemble kernel (K2).
 //
-// One staged Jacobian row holds the column groups
-//   O  (6)  d r / d own block      (the block the pass is segmented by)
-//   T  (6)  d r / d other block
-//   S1 (6)  d r / d (fx fy cx cy k1 k2)
-//   S2 (6)  d r / d (p1 p2 k3) | r | 0 | 0
-//   X  (6)  d r / d body_T_cam           (rig only)
-// and every lane of a thread-group owns one 6x6 product tile  I^T J  of two
-// column groups, accumulated over the 8 residual rows of each observation
-// block and over all blocks of its segment chunk.
+// Every lane of a warp evaluates one tag corner (8 observation blocks x 4
+// corners per warp iteration) and stages its two Jacobian rows in shared
+// memory.  A staged row is cut into column tiles of 8:
+//   E pass:  A = [O(6) fx fy]  B = [cx cy k1 k2 p1 p2 k3 | r]  X = [ext(6) - -] (rig)  C = [T(6) - -]
+//   F pass:  A = [O(6) fx fy]  B = [cx cy k1 k2 p1 p2 k3 | r]  X = [ext(6) - -] (rig)
+// O = d r / d own block (the block the pass is segmented by), T = d r / d other
+// block, r = residual.  The products  tile_I^T tile_J  over the 8 residual rows
+// of a block are FP64 tensor-core MMAs (mma.sync.m8n8k4.f64, k = residual row):
+//   E pass accumulates AA AB BB [AX BX XX] over the chunk and emits AC (the
+//   Schur off-diagonal block W = O^T T) per observation block;
+//   F pass accumulates AA AB [AX].
+// AA = [OO O.s01; . s01.s01], AB = [O.s2-8 g_O; s01.s2-8 g_s01], BB = [s2-8.s2-8 g_s2-8; . sum r^2].
 // ---------------------------------------------------------------------------
-enum Group : int { G_O = 0, G_T = 1, G_S1 = 2, G_S2 = 3, G_X = 4, G_NONE = 7 };
-
 template <bool RIG>
 struct PassGeom {
-  static constexpr int TPB = RIG ? 8 : 5;     // tiles (= lanes) per observation block
-  static constexpr int BPW = RIG ? 4 : 6;     // observation blocks per warp iteration
-  static constexpr int NCOL = RIG ? 30 : 24;  // doubles used per staged row
-  // Row stride in doubles: RS/2 odd so the 4 corner lanes of a block (rows 2t) land in 4 different
-  // 16-byte bank groups; block stride/2 == 1 (mod 8) so the blocks of a warp iteration tile the rest.
-  static constexpr int RS = RIG ? 30 : 26;
-  static constexpr int BLK_STRIDE = 8 * RS + 2;
-  static constexpr int RED_STRIDE = 37;        // epilogue: lane-major, odd stride
-  static constexpr int WARP_SMEM = (BPW * BLK_STRIDE > RED_STRIDE * 32) ? BPW * BLK_STRIDE : RED_STRIDE * 32;  // doubles
+  static constexpr int BPW = 8;               // observation blocks per warp iteration
   static constexpr int SP = RIG ? 15 : 9;     // shared parameters per camera
   static constexpr int WARPS = 4;             // warps (= chunks) per CTA
+  // staged row stride in doubles: == 4 or 12 (mod 16) makes the MMA fragment loads (lane -> row lane%4,
+  // column lane/4) hit 32 distinct banks per half-warp, and the 16-byte row stores of the 4 corner lanes
+  // of a block land in 4 different bank groups
+  static constexpr int RS_E = RIG ? 36 : 28;
+  static constexpr int RS_F = RIG ? 28 : 20;
+  static constexpr int COL_B = 8, COL_X = 16, COL_C = RIG ? 24 : 16;
+  static constexpr int TILES_E = RIG ? 6 : 3;  // accumulated 8x8 tiles per chunk
+  static constexpr int TILES_F = RIG ? 3 : 2;
+  static constexpr int PART_E = TILES_E * 64 + 8;  // doubles per chunk partial; tail slot 0 = robust cost
+  static constexpr int PART_F = TILES_F * 64;
 };
-
-// tile tables: (I group, J group) of tile t in the E pass / F pass
-__host__ __device__ constexpr int tile_I(bool rig, bool epass, int t) {
-  if (!rig) {
-    if (epass) return t < 4 ? G_O : G_S1;                  // OO OT OS1 OS2 S1S1
-    return t < 3 ? G_O : (t == 3 ? G_S1 : G_S2);           // OO OS1 OS2 S1S2 S2S2
-  }
-  if (epass) return t < 5 ? G_O : (t < 7 ? G_S1 : G_X);    // OO OT OS1 OS2 OX S1S1 S1X XX
-  return t < 4 ? G_O : (t == 4 ? G_S1 : (t < 7 ? G_S2 : G_NONE));  // OO OS1 OS2 OX S1S2 S2S2 S2X -
-}
-__host__ __device__ constexpr int tile_J(bool rig, bool epass, int t) {
-  if (!rig) {
-    if (epass) return t == 0 ? G_O : (t == 1 ? G_T : (t == 2 ? G_S1 : (t == 3 ? G_S2 : G_S1)));
-    return t == 0 ? G_O : (t == 1 ? G_S1 : (t == 2 ? G_S2 : (t == 3 ? G_S2 : G_S2)));
-  }
-  if (epass)
-    return t == 0 ? G_O : (t == 1 ? G_T : (t == 2 ? G_S1 : (t == 3 ? G_S2 : (t == 4 ? G_X : (t == 5 ? G_S1 : G_X)))));
-  return t == 0 ? G_O : (t == 1 ? G_S1 : (t == 2 ? G_S2 : (t == 3 ? G_X : (t == 4 ? G_S2 : (t == 5 ? G_S2 : (t == 6 ? G_X : G_NONE))))));
-}
+enum TileE : int { TE_AA = 0, TE_AB = 1, TE_BB = 2, TE_AX = 3, TE_BX = 4, TE_XX = 5 };
+enum TileF : int { TF_AA = 0, TF_AB = 1, TF_AX = 2 };
 
 // one chunk of a pass: `count` consecutive sorted observation blocks that share
 // the own block index and the camera
@@ -78,7 +64,7 @@ struct AssembleArgs {
   const double* shared;   // [n_cam*SP]
   const double* sizes;    // [n_markers]
   // outputs
-  double* partials;       // [n_chunks * TPB * 36]
+  double* partials;       // [n_chunks * PART_E|PART_F]: 8x8 tiles, element (m, n) at m * 8 + n
   double* W;              // [n*36] (E pass only) row-major 6x6: rows own, cols other
   int32_t* fail_flag;     // set to 1 on depth <= 0 / non-finite residual
   int32_t loss;           // 0 trivial, 1 Huber, 2 Cauchy (per tag residual block)
@@ -104,19 +90,16 @@ void launch_finalize_side(bool rig, bool epass, const FinalizeSideArgs& a, cudaS
 
 // per-camera reduction of the shared x shared tiles, gradient and cost
 struct FinalizeSharedArgs {
-  const double* part_e;
-  const double* part_f;
+  const double* part_e;         // the shared x shared tiles all come from the E pass
   const int32_t* cam_chunks_e;  // chunk ids grouped by camera
   const int32_t* cam_ptr_e;     // [n_cam+1]
-  const int32_t* cam_chunks_f;
-  const int32_t* cam_ptr_f;
   int32_t n_cam;
   int32_t n_shared;
   double* Hss;                  // [n_shared*n_shared] block diagonal (zeroed by the kernel)
   double* gs;                   // [n_shared]
   double* cost2_cam;            // [n_cam] sum r^2 per camera
-  double* scratch;              // [n_cam * FIN_SLICES * 6 * 36] first-stage partial tiles
-  int32_t robust;               // 1: cost slot is S2S2[4][4] (sum rho), else S2S2[3][3] (sum r^2)
+  double* scratch;              // [n_cam * FIN_SLICES * PART_E] first-stage partial tiles
+  int32_t robust;               // 1: cost = tail slot (sum rho), else BB[7][7] (sum r^2)
 };
 constexpr int FIN_SLICES = 64;  // CTAs per camera in the first stage of finalize_shared
 void launch_finalize_shared(bool rig, const FinalizeSharedArgs& a, cudaStream_t s);

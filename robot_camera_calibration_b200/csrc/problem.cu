@@ -192,7 +192,7 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
   const int32_t* e_of = P->elim_view ? view_idx : marker_idx;
   const int32_t* f_of = P->elim_view ? marker_idx : view_idx;
   const int bpw = P->rig ? PassGeom<true>::BPW : PassGeom<false>::BPW;
-  const int ch_max = std::max(bpw, env_int("RCC_CHUNK", 60));
+  const int ch_max = std::max(bpw, env_int("RCC_CHUNK", 64));
   cudaStream_t s = P->stream;
 
   // ---- E pass order
@@ -334,9 +334,8 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
   }
 
   // ---- buffers that scale with the observations
-  const int tpb = P->rig ? PassGeom<true>::TPB : PassGeom<false>::TPB;
-  P->part_e.alloc((size_t)P->n_chunks_e * tpb * 36);
-  P->part_f.alloc((size_t)P->n_chunks_f * tpb * 36);
+  P->part_e.alloc((size_t)P->n_chunks_e * (P->rig ? PassGeom<true>::PART_E : PassGeom<false>::PART_E));
+  P->part_f.alloc((size_t)P->n_chunks_f * (P->rig ? PassGeom<true>::PART_F : PassGeom<false>::PART_F));
   P->W.alloc((size_t)n * 36);
   P->Y.alloc((size_t)std::max<int64_t>(P->n_pairs, 1) * 36);
   P->cost_partials.alloc((size_t)std::max(1, eval_grid(n)));
@@ -417,8 +416,7 @@ static void do_linearize(P_t* P) {
     launch_finalize_side(P->rig, true, fe, P->stream);
     FinalizeSideArgs ff{P->part_f.p, P->f_chunks.p, P->f_chunk_ptr.p, P->n_f, P->n_shared, P->Hff.p, P->gf.p, P->Hfs.p};
     launch_finalize_side(P->rig, false, ff, P->stream);
-    FinalizeSharedArgs fs{P->part_e.p, P->part_f.p, P->cam_chunks_e.p, P->cam_ptr_e.p, P->cam_chunks_f.p,
-                          P->cam_ptr_f.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p, P->fin_scratch.p,
+    FinalizeSharedArgs fs{P->part_e.p, P->cam_chunks_e.p, P->cam_ptr_e.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p, P->fin_scratch.p,
                           P->loss != 0 ? 1 : 0};
     launch_finalize_shared(P->rig, fs, P->stream);
   }
@@ -808,7 +806,7 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     P->c_intr.assign(P->n_cam, 0); P->c_dist.assign(P->n_cam, 0); P->c_ext.assign(P->n_cam, 0);
     P->Hee.alloc((size_t)P->n_e * 36); P->ge.alloc((size_t)P->n_e * 6); P->Hes.alloc((size_t)P->n_e * 6 * P->n_shared);
     P->Hff.alloc((size_t)P->n_f * 36); P->gf.alloc((size_t)P->n_f * 6); P->Hfs.alloc((size_t)P->n_f * 6 * P->n_shared);
-    P->fin_scratch.alloc((size_t)P->n_cam * FIN_SLICES * 6 * 36);
+    P->fin_scratch.alloc((size_t)P->n_cam * FIN_SLICES * PassGeom<true>::PART_E);
     P->Hss.alloc((size_t)P->n_shared * P->n_shared); P->gs.alloc((size_t)P->n_shared); P->cost2_cam.alloc(P->n_cam);
     P->Linv.alloc((size_t)P->n_e * 36); P->Yb.alloc((size_t)P->n_e * P->n_bb * 36); P->d2e.alloc((size_t)P->n_e * 6);
     P->S.alloc((size_t)(P->n_red + 3) * P->ld); P->S.zero(s);
