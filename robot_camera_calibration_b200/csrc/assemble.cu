@@ -298,12 +298,11 @@ void launch_assemble(bool rig, bool epass, bool own_is_view, const AssembleArgs&
 // j >= 7 -> H_os[r][shared parameter j - 7] (kept per camera).
 // ---------------------------------------------------------------------------
 template <bool RIG, bool EPASS>
-__global__ void __launch_bounds__(160) finalize_side_kernel(const FinalizeSideArgs a) {
+__device__ __forceinline__ void finalize_side_body(const FinalizeSideArgs& a, int i) {
   using PG = PassGeom<RIG>;
   constexpr int SP = PG::SP, NJ = 7 + SP;
   constexpr int PART = EPASS ? PG::PART_E : PG::PART_F;
   constexpr int T_AX = EPASS ? (int)TE_AX : (int)TF_AX;
-  const int i = blockIdx.x;
   const int tid = threadIdx.x;
   double* hos = a.Hos + (size_t)i * 6 * a.n_shared;
   for (int k = tid; k < 6 * a.n_shared; k += blockDim.x) hos[k] = 0.0;
@@ -318,35 +317,36 @@ __global__ void __launch_bounds__(160) finalize_side_kernel(const FinalizeSideAr
   else if (j < 16) src = TE_AB * 64 + r * 8 + (j - 9);      // cx .. k3: columns 0..6 of tile B
   else src = T_AX * 64 + r * 8 + (j - 16);                  // rig extrinsics
   const int c0 = a.chunk_ptr[i], c1 = a.chunk_ptr[i + 1];
+  const double* __restrict__ part = a.partials + src;
+  const Chunk* __restrict__ chunks = a.chunks;
   double total = 0.0, per_cam = 0.0;
-  int cam = (c0 < c1) ? a.chunks[c0].cam : 0;
-  for (int c = c0; c < c1; ++c) {
-    const int cm = a.chunks[c].cam;
-    if (cm != cam) {
-      if (j >= 7) hos[r * a.n_shared + cam * SP + (j - 7)] = per_cam;
-      per_cam = 0.0;
-      cam = cm;
+  int cam = (c0 < c1) ? chunks[c0].cam : 0;
+  for (int cb = c0; cb < c1; cb += 8) {
+    // independent loads of up to 8 chunks first, then the ordered sums
+    double v[8];
+    int cm[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = min(cb + u, c1 - 1);
+      v[u] = part[(size_t)c * PART];
+      cm[u] = chunks[c].cam;
     }
-    const double v = a.partials[(size_t)c * PART + src];
-    total += v;
-    per_cam += v;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (cb + u < c1) {
+        if (cm[u] != cam) {
+          if (j >= 7) hos[r * a.n_shared + cam * SP + (j - 7)] = per_cam;
+          per_cam = 0.0;
+          cam = cm[u];
+        }
+        total += v[u];
+        per_cam += v[u];
+      }
+    }
   }
   if (c0 < c1 && j >= 7) hos[r * a.n_shared + cam * SP + (j - 7)] = per_cam;
   if (j < 6) a.Hoo[(size_t)i * 36 + r * 6 + j] = total;
   if (j == 6) a.go[(size_t)i * 6 + r] = total;
-}
-
-void launch_finalize_side(bool rig, bool epass, const FinalizeSideArgs& a, cudaStream_t s) {
-  if (a.n_own == 0) return;
-  const int grid = a.n_own;
-  if (rig) {
-    if (epass) finalize_side_kernel<true, true><<<grid, 160, 0, s>>>(a);
-    else finalize_side_kernel<true, false><<<grid, 160, 0, s>>>(a);
-  } else {
-    if (epass) finalize_side_kernel<false, true><<<grid, 160, 0, s>>>(a);
-    else finalize_side_kernel<false, false><<<grid, 160, 0, s>>>(a);
-  }
-  RCC_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------
@@ -357,16 +357,35 @@ void launch_finalize_side(bool rig, bool epass, const FinalizeSideArgs& a, cudaS
 // H_ss / g_s / cost.
 // ---------------------------------------------------------------------------
 template <bool RIG>
-__global__ void __launch_bounds__(256) finalize_shared_partial_kernel(const FinalizeSharedArgs a) {
-  constexpr int PART = PassGeom<RIG>::PART_E;
-  const int slice = blockIdx.x, cam = blockIdx.y;
-  const int32_t* list = a.cam_chunks_e + a.cam_ptr_e[cam];
+__device__ __forceinline__ void finalize_shared_partial_body(const FinalizeSharedArgs& a, int slice, int cam) {
+  // warp w of the CTA takes chunks lo + w, lo + w + 8, ... of the slice; lane l keeps elements l, l + 32, ...
+  // of the partial in registers; the 8 warp sums are then added in warp order.
+  constexpr int PART = PassGeom<RIG>::PART_E, NR = (PART + 31) / 32;
+  __shared__ double red[8][PART];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t* __restrict__ list = a.cam_chunks_e + a.cam_ptr_e[cam];
+  const double* __restrict__ part = a.part_e;
   const int n = a.cam_ptr_e[cam + 1] - a.cam_ptr_e[cam];
   const int per = (n + FIN_SLICES - 1) / FIN_SLICES;
   const int lo = slice * per, hi = min(n, lo + per);
+  double acc[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+#pragma unroll 2
+  for (int c = lo + warp; c < hi; c += 8) {
+    const double* src = part + (size_t)list[c] * PART;
+#pragma unroll
+    for (int j = 0; j < NR; ++j)
+      if (lane + 32 * j < PART) acc[j] += src[lane + 32 * j];
+  }
+#pragma unroll
+  for (int j = 0; j < NR; ++j)
+    if (lane + 32 * j < PART) red[warp][lane + 32 * j] = acc[j];
+  __syncthreads();
   for (int k = threadIdx.x; k < PART; k += blockDim.x) {
     double s = 0.0;
-    for (int c = lo; c < hi; ++c) s += a.part_e[(size_t)list[c] * PART + k];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][k];
     a.scratch[((size_t)cam * FIN_SLICES + slice) * PART + k] = s;
   }
 }
@@ -402,6 +421,7 @@ __global__ void __launch_bounds__(256) finalize_shared_final_kernel(const Finali
   for (int k = tid; k < SP * ns; k += blockDim.x) H[(size_t)base * ns + k] = 0.0;
   for (int k = tid; k < PART; k += blockDim.x) {
     double s = 0.0;
+#pragma unroll 16
     for (int sl = 0; sl < FIN_SLICES; ++sl) s += a.scratch[((size_t)cam * FIN_SLICES + sl) * PART + k];
     tot[k] = s;
   }
@@ -418,14 +438,33 @@ __global__ void __launch_bounds__(256) finalize_shared_final_kernel(const Finali
   if (tid == 0) a.cost2_cam[cam] = a.robust ? tot[PassGeom<RIG>::TILES_E * 64] : tot[TE_BB * 64 + 7 * 8 + 7];
 }
 
-void launch_finalize_shared(bool rig, const FinalizeSharedArgs& a, cudaStream_t s) {
-  dim3 grid(FIN_SLICES, a.n_cam);
+// one launch for the three independent reductions, longest CTAs first: the (slice, camera) first stage of
+// finalize_shared, then the F side (many chunks per kept block), then the E side
+template <bool RIG>
+__global__ void __launch_bounds__(256) finalize_fused_kernel(const FinalizeSideArgs e, const FinalizeSideArgs f,
+                                                             const FinalizeSharedArgs sh) {
+  int i = blockIdx.x;
+  if (i < FIN_SLICES * sh.n_cam) {
+    finalize_shared_partial_body<RIG>(sh, i % FIN_SLICES, i / FIN_SLICES);
+    return;
+  }
+  i -= FIN_SLICES * sh.n_cam;
+  if (i < f.n_own) {
+    finalize_side_body<RIG, false>(f, i);
+    return;
+  }
+  finalize_side_body<RIG, true>(e, i - f.n_own);
+}
+
+void launch_finalize(bool rig, const FinalizeSideArgs& e, const FinalizeSideArgs& f, const FinalizeSharedArgs& sh,
+                     cudaStream_t s) {
+  const int grid = e.n_own + f.n_own + FIN_SLICES * sh.n_cam;
   if (rig) {
-    finalize_shared_partial_kernel<true><<<grid, 256, 0, s>>>(a);
-    finalize_shared_final_kernel<true><<<a.n_cam, 256, 0, s>>>(a);
+    finalize_fused_kernel<true><<<grid, 256, 0, s>>>(e, f, sh);
+    finalize_shared_final_kernel<true><<<sh.n_cam, 256, 0, s>>>(sh);
   } else {
-    finalize_shared_partial_kernel<false><<<grid, 256, 0, s>>>(a);
-    finalize_shared_final_kernel<false><<<a.n_cam, 256, 0, s>>>(a);
+    finalize_fused_kernel<false><<<grid, 256, 0, s>>>(e, f, sh);
+    finalize_shared_final_kernel<false><<<sh.n_cam, 256, 0, s>>>(sh);
   }
   RCC_CUDA(cudaGetLastError());
 }

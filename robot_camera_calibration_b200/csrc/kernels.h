@@ -86,7 +86,6 @@ struct FinalizeSideArgs {
   double* go;                // [n_own*6]
   double* Hos;               // [n_own*6*n_shared]  (zeroed by the kernel)
 };
-void launch_finalize_side(bool rig, bool epass, const FinalizeSideArgs& a, cudaStream_t s);
 
 // per-camera reduction of the shared x shared tiles, gradient and cost
 struct FinalizeSharedArgs {
@@ -102,7 +101,9 @@ struct FinalizeSharedArgs {
   int32_t robust;               // 1: cost = tail slot (sum rho), else BB[7][7] (sum r^2)
 };
 constexpr int FIN_SLICES = 64;  // CTAs per camera in the first stage of finalize_shared
-void launch_finalize_shared(bool rig, const FinalizeSharedArgs& a, cudaStream_t s);
+// E side, F side and the first stage of the shared reduction in one launch, then the per-camera final stage
+void launch_finalize(bool rig, const FinalizeSideArgs& e, const FinalizeSideArgs& f, const FinalizeSharedArgs& sh,
+                     cudaStream_t s);
 
 // pose expansion: rvec,t -> R, Jr, t
 void launch_expand_poses(const double* views, int n_views, double* view_x, const double* markers,

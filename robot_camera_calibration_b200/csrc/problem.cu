@@ -411,14 +411,12 @@ static void do_linearize(P_t* P) {
     launch_assemble(P->rig, false, !P->elim_view, a, P->stream);
   }
   {
-    Scoped t(P, ST_FINALIZE, 4);
+    Scoped t(P, ST_FINALIZE, 2);
     FinalizeSideArgs fe{P->part_e.p, P->e_chunks.p, P->e_chunk_ptr.p, P->n_e, P->n_shared, P->Hee.p, P->ge.p, P->Hes.p};
-    launch_finalize_side(P->rig, true, fe, P->stream);
     FinalizeSideArgs ff{P->part_f.p, P->f_chunks.p, P->f_chunk_ptr.p, P->n_f, P->n_shared, P->Hff.p, P->gf.p, P->Hfs.p};
-    launch_finalize_side(P->rig, false, ff, P->stream);
     FinalizeSharedArgs fs{P->part_e.p, P->cam_chunks_e.p, P->cam_ptr_e.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p, P->fin_scratch.p,
                           P->loss != 0 ? 1 : 0};
-    launch_finalize_shared(P->rig, fs, P->stream);
+    launch_finalize(P->rig, fe, ff, fs, P->stream);
   }
   P->linearized = true;
   P->schur_done = P->step_ready = P->cand_ready = false;
