@@ -39,6 +39,7 @@ UNIT = "observations/s"
 BYTES_PER_BLOCK_E = 64 + 4 + 288          # pixels + other index in, cross block W out
 BYTES_PER_BLOCK_F = 64 + 4
 FLOP_PER_BLOCK = 2 * 8 * 253 + 1400       # J^T J products (253 unique entries x 8 rows) + Jacobian evaluation
+NCU_DRAM_BYTES_E_PASS = 32313856 + 89391616   # measured once under ncu (cfg2, 454 996 blocks)
 
 
 def workload(cfg, rank, scale):
@@ -342,7 +343,11 @@ def run_ours(args):
                        "timing": "CUDA events per step on the library's stream, summed; max over ranks"},
             "roofline": {"bound": "hbm", "kernel": "assemble_kernel<E pass> (fused residual+Jacobian+J^T J tiles)",
                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_DRAM_BYTES_E_PASS if (args.config == 2 and args.scale == 1.0) else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one E-pass "
+                                           "launch on this workload (profiles/r1_ncu_k2_dmma_summary.txt); below the "
+                                           "algorithmic bytes because part of W is still in L2 when the kernel ends",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_BLOCK_E * n_blocks,
                          "kernel_ms": k_ms, "f_pass_kernel_ms": kf_ms,
                          "note": "fused assembly is FP64-pipe-bound, not HBM-bound: see roofline_fp64"},

@@ -90,7 +90,7 @@ struct WarpSmem {
 };
 
 template <bool RIG, bool EPASS, bool OWN_IS_VIEW, bool LOSS>
-__global__ void __launch_bounds__(PassGeom<RIG>::WARPS * 32, RCC_K2_MIN_CTAS)
+__global__ void __launch_bounds__(PassGeom<RIG>::WARPS * 32, (RIG && EPASS) ? 2 : RCC_K2_MIN_CTAS)   // rig E pass: 89 KB smem per CTA
 assemble_kernel(const AssembleArgs a) {
   using PG = PassGeom<RIG>;
   using WS = WarpSmem<RIG, EPASS>;
