@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>

@@ -2,11 +2,16 @@
 // Jacobians in the Ceres CostFunction::Evaluate layout), and K6's cost-only
 // evaluation used for the LM gain ratio.
 //
-// One thread per tag corner (4 threads = one observation block); each thread
-// writes its two residual rows of every Jacobian block as 16-byte vector
-// stores.  The kernel is HBM-write-bound: 1 408 B out per 72 B in.  Rows are staged in shared
-// memory in the Ceres layout and leave the SM as TMA bulk copies (cp.async.bulk, one per
-// (tag, Jacobian block) record).
+// One thread per tag corner (4 lanes = one observation block, a warp = a group
+// of 8 blocks); persistent warps walk the groups with the next group's indices
+// and pixels prefetched into registers.  The kernel is HBM-write-bound: 1 408 B
+// out per 72 B in.  A group's rows are staged in shared memory array-major
+// ([array][8 blocks][rows x cols], the Ceres layout of 8 consecutive residual
+// blocks) and leave the SM as TMA bulk copies (cp.async.bulk, SASS UBLKCP): one
+// copy of 0.5-3 KB per output array when the 8 blocks are consecutive in caller
+// order, one per (block, array) otherwise.  The copies of group i drain while
+// group i+1 is gathered and evaluated (wait_group.read sits right before the
+// staging buffer is written again).
 #include "common.cuh"
 #include "kernels.h"
 #include "model.cuh"
@@ -14,8 +19,13 @@
 namespace rcc {
 
 constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_CTAS_PER_SM = 2;   // 128 registers x 256 threads; 91 KB staging per CTA
 
-int eval_grid(int64_t n) { return ceil_div(n * 4, EVAL_THREADS); }
+int eval_grid(int64_t n) {
+  const int64_t groups = (n + 7) / 8;
+  return (int)std::max<int64_t>(1, std::min<int64_t>((groups + EVAL_THREADS / 32 - 1) / (EVAL_THREADS / 32),
+                                                     (int64_t)NUM_SMS_B200 * EVAL_CTAS_PER_SM));
+}
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
 #pragma unroll
@@ -30,11 +40,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;  // valid on thread 0
 }
 
-// per-block staging record (doubles): res[8] | intr[8][4] | dist[8][5] | view[8][6] | marker[8][6] | ext[8][6]
+// per-warp staging (doubles), array-major: res[8][8] | intr[8][8x4] | dist[8][8x5] | view[8][8x6] | marker[8][8x6] | ext[8][8x6]
 template <bool RIG>
 struct EvalRec {
-  static constexpr int RES = 0, JI = 8, JD = 40, JV = 80, JM = 128, JX = 176;
-  static constexpr int SIZE = RIG ? 226 : 178;   // +2: consecutive records shift by 16 B across the smem banks
+  static constexpr int RES = 0, JI = 64, JD = 320, JV = 640, JM = 1024, JX = 1408;
+  static constexpr int SIZE = RIG ? 1792 : 1408;
 };
 
 // TMA bulk copy shared::cta -> global (16-byte aligned, size a multiple of 16); SASS: UBLKCP
@@ -44,121 +54,158 @@ __device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int
                : "memory");
 }
 
+struct EvalIdx {      // raw loads only: nothing here may wait on memory when the next group is prefetched
+  int vi, mi, cam;
+  int o;          // caller position of the block
+  double2 px;
+  bool on;
+};
+
 template <bool RIG, bool WANT_J>
-__global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const EvalArgs a) {
+__global__ void __launch_bounds__(EVAL_THREADS, EVAL_CTAS_PER_SM) evaluate_kernel(const EvalArgs a) {
   using ER = EvalRec<RIG>;
-  __shared__ double red[EVAL_THREADS / 32];
-  extern __shared__ __align__(16) double stage[];   // WANT_J: [warps][8 blocks][ER::SIZE]; [warps][8] caller positions
-  const int64_t tid = (int64_t)blockIdx.x * EVAL_THREADS + threadIdx.x;
-  const int64_t g = tid >> 2;
-  const int t = (int)(tid & 3);
+  constexpr int SP = RIG ? 15 : 9;
+  constexpr int WPC = EVAL_THREADS / 32;
+  __shared__ double red[WPC];
+  extern __shared__ __align__(128) double stage[];   // WANT_J: [warps][ER::SIZE]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double r2 = 0.0;
-  double* wrec = WANT_J ? stage + (size_t)warp * 8 * ER::SIZE : nullptr;
-  int64_t* wpos = WANT_J ? reinterpret_cast<int64_t*>(stage + (size_t)(EVAL_THREADS / 32) * 8 * ER::SIZE) + warp * 8 : nullptr;
-  if (g < a.n) {
-    const int vi = a.view_idx[g], mi = a.marker_idx[g], cam = a.cam[g];
-    constexpr int SP = RIG ? 15 : 9;
-    // expanded pose records as 16-byte loads (the 4 corner lanes of a tag read the same lines)
-    double vx[POSEX], mx[POSEX], xx[POSEX];
-    {
-      const double2* pv = reinterpret_cast<const double2*>(a.view_x + (size_t)vi * POSEX);
-      const double2* pm = reinterpret_cast<const double2*>(a.marker_x + (size_t)mi * POSEX);
-#pragma unroll
-      for (int k = 0; k < 11; ++k) {
-        const double2 u = pv[k], w = pm[k];
-        vx[2 * k] = u.x; vx[2 * k + 1] = u.y;
-        mx[2 * k] = w.x; mx[2 * k + 1] = w.y;
-      }
-      if (RIG) {
-        const double2* pe = reinterpret_cast<const double2*>(a.ext_x + (size_t)cam * POSEX);
+  const int q = lane >> 2, t = lane & 3;
+  double* wrec = WANT_J ? stage + (size_t)warp * ER::SIZE : nullptr;
+  const int64_t n_groups = (a.n + 7) >> 3;
+  const int64_t gw = (int64_t)blockIdx.x * WPC + warp, nw = (int64_t)gridDim.x * WPC;
+  double cost = 0.0;
+
+  auto load_idx = [&](int64_t grp) -> EvalIdx {
+    EvalIdx x;
+    const int64_t g = grp * 8 + q;
+    x.on = grp < n_groups && g < a.n;
+    x.vi = x.mi = x.cam = x.o = 0;
+    x.px = make_double2(0.0, 0.0);
+    if (x.on) {
+      x.vi = a.view_idx[g];
+      x.mi = a.marker_idx[g];
+      x.cam = a.cam[g];
+      x.o = a.orig ? a.orig[g] : (int)g;
+      x.px = *reinterpret_cast<const double2*>(a.pix + g * 8 + 2 * t);
+    }
+    return x;
+  };
+
+  EvalIdx cur = load_idx(gw);
+  for (int64_t grp = gw; grp < n_groups; grp += nw) {
+    const EvalIdx nxt = load_idx(grp + nw);   // in flight during this group's arithmetic
+    CornerRows<RIG> c;
+    double r2 = 0.0;
+    if (cur.on) {
+      // expanded pose records as 16-byte loads (the 4 corner lanes of a tag read the same lines)
+      double vx[POSEX], mx[POSEX], xx[POSEX];
+      {
+        const double2* pv = reinterpret_cast<const double2*>(a.view_x + (size_t)cur.vi * POSEX);
+        const double2* pm = reinterpret_cast<const double2*>(a.marker_x + (size_t)cur.mi * POSEX);
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
-          const double2 u = pe[k];
-          xx[2 * k] = u.x; xx[2 * k + 1] = u.y;
+          const double2 u = pv[k], w = pm[k];
+          vx[2 * k] = u.x; vx[2 * k + 1] = u.y;
+          mx[2 * k] = w.x; mx[2 * k + 1] = w.y;
+        }
+        if (RIG) {
+          const double2* pe = reinterpret_cast<const double2*>(a.ext_x + (size_t)cur.cam * POSEX);
+#pragma unroll
+          for (int k = 0; k < 11; ++k) {
+            const double2 u = pe[k];
+            xx[2 * k] = u.x; xx[2 * k + 1] = u.y;
+          }
         }
       }
+      BlockGeom<RIG> geo;
+      block_geometry<RIG>(vx, mx, RIG ? xx : nullptr, geo);
+      double ox, oy;
+      corner_xy(t, mx[PX_HS], ox, oy);
+      eval_corner<RIG, WANT_J>(geo, a.shared + (size_t)cur.cam * SP, ox, oy, cur.px.x, cur.px.y, c);
+      if (!(c.depth > 0.0) || !isfinite(c.r[0]) || !isfinite(c.r[1])) *a.fail_flag = 1;
+      r2 = c.r[0] * c.r[0] + c.r[1] * c.r[1];
+      if (!WANT_J && a.residuals)
+        *reinterpret_cast<double2*>(a.residuals + (int64_t)cur.o * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
     }
-    BlockGeom<RIG> geo;
-    block_geometry<RIG>(vx, mx, RIG ? xx : nullptr, geo);
-    double ox, oy;
-    corner_xy(t, mx[PX_HS], ox, oy);
-    const double2 px = *reinterpret_cast<const double2*>(a.pix + g * 8 + 2 * t);
-    CornerRows<RIG> c;
-    eval_corner<RIG, WANT_J>(geo, a.shared + (size_t)cam * SP, ox, oy, px.x, px.y, c);
-    if (!(c.depth > 0.0) || !isfinite(c.r[0]) || !isfinite(c.r[1])) *a.fail_flag = 1;
-    r2 = c.r[0] * c.r[0] + c.r[1] * c.r[1];
-    const int64_t o = a.orig ? (int64_t)a.orig[g] : g;
-    if (!WANT_J) {
-      if (a.residuals) *reinterpret_cast<double2*>(a.residuals + o * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
-    } else {
-      // stage the corner's two rows of every block in Ceres layout
-      double* rec = wrec + (lane >> 2) * ER::SIZE;
-      if (t == 0) wpos[lane >> 2] = o;
-      *reinterpret_cast<double2*>(rec + ER::RES + 2 * t) = make_double2(c.r[0], c.r[1]);
-      double2* d = reinterpret_cast<double2*>(rec + ER::JI + 8 * t);
-      d[0] = make_double2(c.js[0][0], c.js[0][1]);
-      d[1] = make_double2(c.js[0][2], c.js[0][3]);
-      d[2] = make_double2(c.js[1][0], c.js[1][1]);
-      d[3] = make_double2(c.js[1][2], c.js[1][3]);
-      d = reinterpret_cast<double2*>(rec + ER::JD + 10 * t);
-      d[0] = make_double2(c.js[0][4], c.js[0][5]);
-      d[1] = make_double2(c.js[0][6], c.js[0][7]);
-      d[2] = make_double2(c.js[0][8], c.js[1][4]);
-      d[3] = make_double2(c.js[1][5], c.js[1][6]);
-      d[4] = make_double2(c.js[1][7], c.js[1][8]);
-      d = reinterpret_cast<double2*>(rec + ER::JV + 12 * t);
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jv[i][2 * j], c.jv[i][2 * j + 1]);
-      d = reinterpret_cast<double2*>(rec + ER::JM + 12 * t);
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jm[i][2 * j], c.jm[i][2 * j + 1]);
-      if (RIG) {
-        d = reinterpret_cast<double2*>(rec + ER::JX + 12 * t);
+    if (WANT_J) {
+      // the previous group's bulk copies must have read the staging buffer before it is rewritten
+#ifndef RCC_K1_NOWAIT_EXPERIMENT
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+      __syncwarp();
+      if (cur.on) {
+        // stage the corner's two rows of every Jacobian block in Ceres layout
+        *reinterpret_cast<double2*>(wrec + ER::RES + q * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
+        double2* d = reinterpret_cast<double2*>(wrec + ER::JI + q * 32 + 8 * t);
+        d[0] = make_double2(c.js[0][0], c.js[0][1]);
+        d[1] = make_double2(c.js[0][2], c.js[0][3]);
+        d[2] = make_double2(c.js[1][0], c.js[1][1]);
+        d[3] = make_double2(c.js[1][2], c.js[1][3]);
+        d = reinterpret_cast<double2*>(wrec + ER::JD + q * 40 + 10 * t);
+        d[0] = make_double2(c.js[0][4], c.js[0][5]);
+        d[1] = make_double2(c.js[0][6], c.js[0][7]);
+        d[2] = make_double2(c.js[0][8], c.js[1][4]);
+        d[3] = make_double2(c.js[1][5], c.js[1][6]);
+        d[4] = make_double2(c.js[1][7], c.js[1][8]);
+        d = reinterpret_cast<double2*>(wrec + ER::JV + q * 48 + 12 * t);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jx[i][2 * j], c.jx[i][2 * j + 1]);
+          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jv[i][2 * j], c.jv[i][2 * j + 1]);
+        d = reinterpret_cast<double2*>(wrec + ER::JM + q * 48 + 12 * t);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jm[i][2 * j], c.jm[i][2 * j + 1]);
+        if (RIG) {
+          d = reinterpret_cast<double2*>(wrec + ER::JX + q * 48 + 12 * t);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jx[i][2 * j], c.jx[i][2 * j + 1]);
+        }
       }
-    }
-  }
-  if (WANT_J) {
-    // hand the copy-out to the TMA engine: one bulk copy (shared -> global) per (block, array)
-    // record, 64..384 contiguous bytes each, issued by one lane per record
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the async proxy
-    __syncwarp();
-    const int64_t g0 = ((int64_t)blockIdx.x * EVAL_THREADS + warp * 32) >> 2;
-    const int nblk = (int)max((int64_t)0, min((int64_t)8, a.n - g0));
-    constexpr int NARR = RIG ? 6 : 5;
-    for (int idx = lane; idx < nblk * NARR; idx += 32) {
-      const int q = idx / NARR, arr = idx - q * NARR;
-      double* dst = nullptr;
-      int off = 0, k = 0;
-      switch (arr) {
-        case 0: dst = a.residuals; off = ER::RES; k = 8; break;
-        case 1: dst = a.jac_intr; off = ER::JI; k = 32; break;
-        case 2: dst = a.jac_dist; off = ER::JD; k = 40; break;
-        case 3: dst = a.jac_view; off = ER::JV; k = 48; break;
-        case 4: dst = a.jac_marker; off = ER::JM; k = 48; break;
-        default: dst = a.jac_ext; off = ER::JX; k = 48; break;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the async proxy
+      __syncwarp();
+      // hand the copy-out to the TMA engine
+      const int nblk = (int)min((int64_t)8, a.n - grp * 8);
+      const int o0 = __shfl_sync(0xffffffffu, cur.o, 0);
+      const bool run = __all_sync(0xffffffffu, !cur.on || cur.o == o0 + q);   // 8 consecutive caller positions
+      constexpr int NARR = RIG ? 6 : 5;
+      const int n_copies = run ? NARR : nblk * NARR;
+      for (int idx = lane; idx < ((n_copies + 31) & ~31); idx += 32) {   // uniform trip count: shuffles inside
+        const int qq = run ? 0 : idx / NARR, arr = run ? idx : idx - qq * NARR;
+        const int64_t o = __shfl_sync(0xffffffffu, cur.o, (qq & 7) * 4);
+        double* dst = nullptr;
+        int off = 0, k = 0;
+        switch (arr) {
+          case 0: dst = a.residuals; off = ER::RES; k = 8; break;
+          case 1: dst = a.jac_intr; off = ER::JI; k = 32; break;
+          case 2: dst = a.jac_dist; off = ER::JD; k = 40; break;
+          case 3: dst = a.jac_view; off = ER::JV; k = 48; break;
+          case 4: dst = a.jac_marker; off = ER::JM; k = 48; break;
+          default: dst = a.jac_ext; off = ER::JX; k = 48; break;
+        }
+#ifdef RCC_K1_EXPERIMENT_ARR
+        if (arr != RCC_K1_EXPERIMENT_ARR) dst = nullptr;   // timing experiment: only one output array is written
+#endif
+        if (idx < n_copies && dst)
+          bulk_store(dst + o * k, wrec + off + qq * k, (run ? nblk : 1) * k * (int)sizeof(double));
       }
-      if (dst) bulk_store(dst + wpos[q] * k, wrec + q * ER::SIZE + off, k * (int)sizeof(double));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+    if (a.loss != 0) {
+      // the 4 corner threads of a tag are adjacent lanes: rho(sum of the 8 squared residuals) / 4 each
+      double sb = r2 + __shfl_xor_sync(0xffffffffu, r2, 1);
+      sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+      double rho1;
+      r2 = cur.on ? 0.25 * robust_rho(a.loss, a.loss_a2, sb, rho1) : 0.0;
+    }
+    cost += r2;
+    cur = nxt;
   }
-  if (a.loss != 0) {
-    // the 4 corner threads of a tag are adjacent lanes: rho(sum of the 8 squared residuals) / 4 each
-    double sb = r2 + __shfl_xor_sync(0xffffffffu, r2, 1);
-    sb += __shfl_xor_sync(0xffffffffu, sb, 2);
-    double rho1;
-    r2 = (g < a.n) ? 0.25 * robust_rho(a.loss, a.loss_a2, sb, rho1) : 0.0;
-  }
-  const double s = block_sum(r2, red);
+  if (WANT_J) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+  const double s = block_sum(cost, red);
   if (threadIdx.x == 0 && a.cost2_partials) a.cost2_partials[blockIdx.x] = s;
 }
 
@@ -166,7 +213,7 @@ template <bool RIG, bool WANT_J>
 static void launch_evaluate_t(const EvalArgs& a, cudaStream_t s) {
   const int grid = eval_grid(a.n);
   size_t smem = 0;
-  if (WANT_J) smem = (size_t)(EVAL_THREADS / 32) * 8 * (EvalRec<RIG>::SIZE * sizeof(double) + sizeof(int64_t));
+  if (WANT_J) smem = (size_t)(EVAL_THREADS / 32) * EvalRec<RIG>::SIZE * sizeof(double);
   auto k = evaluate_kernel<RIG, WANT_J>;
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
@@ -177,15 +224,211 @@ static void launch_evaluate_t(const EvalArgs& a, cudaStream_t s) {
   RCC_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------
+// materialise_kernel: K1 proper.  Same chunk pipeline as the fused kernel K2 (one warp per
+// (own block, camera) chunk, own pose in shared memory, other-pose records prefetched by
+// cp.async one iteration ahead, lane 4b+t evaluates corner t of block b and streams its
+// rows to shared memory as soon as a column group is complete), but the staged rows are
+// the Ceres layout and leave the SM as TMA bulk copies instead of feeding MMAs.
+// ---------------------------------------------------------------------------
+template <bool RIG, bool OWN_IS_VIEW>
+struct CeresSink {
+  using ER = EvalRec<RIG>;
+  double* rec;   // warp staging
+  int q, t;      // block of the group, corner
+  double d0[5];  // distortion row of the u residual waits for the v row: 10 contiguous doubles
+  __device__ __forceinline__ void put6(int off, int i, const double* v) {
+    double2* d = reinterpret_cast<double2*>(rec + off + q * 48 + (2 * t + i) * 6);
+    d[0] = make_double2(v[0], v[1]);
+    d[1] = make_double2(v[2], v[3]);
+    d[2] = make_double2(v[4], v[5]);
+  }
+  __device__ __forceinline__ void shared(int i, const double* js, double r) {
+    double2* d = reinterpret_cast<double2*>(rec + ER::JI + q * 32 + (2 * t + i) * 4);
+    d[0] = make_double2(js[0], js[1]);
+    d[1] = make_double2(js[2], js[3]);
+    rec[ER::RES + q * 8 + 2 * t + i] = r;
+    if (i == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) d0[k] = js[4 + k];
+    } else {
+      d = reinterpret_cast<double2*>(rec + ER::JD + q * 40 + 10 * t);
+      d[0] = make_double2(d0[0], d0[1]);
+      d[1] = make_double2(d0[2], d0[3]);
+      d[2] = make_double2(d0[4], js[4]);
+      d[3] = make_double2(js[5], js[6]);
+      d[4] = make_double2(js[7], js[8]);
+    }
+  }
+  __device__ __forceinline__ void marker(int i, const double* jm) { put6(ER::JM, i, jm); }
+  __device__ __forceinline__ void view(int i, const double* jv) { put6(ER::JV, i, jv); }
+  __device__ __forceinline__ void ext(int i, const double* jx) { put6(ER::JX, i, jx); }
+};
+
+__device__ __forceinline__ void ev_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+constexpr int MAT_WARPS = 4;
+template <bool RIG>
+struct MatSmem {   // per warp, doubles
+  static constexpr int STAGE = EvalRec<RIG>::SIZE;          // other-pose records [2][8][POSEX]
+  static constexpr int CONSTS = STAGE + 2 * 8 * POSEX;      // own pose, ext pose, shared parameters
+  static constexpr int TOTAL = CONSTS + 2 * POSEX + 16;
+};
+
+template <bool RIG, bool OWN_IS_VIEW>
+__global__ void __launch_bounds__(MAT_WARPS * 32, 3) materialise_kernel(const EvalArgs a) {
+  using ER = EvalRec<RIG>;
+  using MS = MatSmem<RIG>;
+  constexpr int SP = RIG ? 15 : 9, BPW = 8;
+  extern __shared__ __align__(128) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk_id = blockIdx.x * MAT_WARPS + warp;
+  if (chunk_id >= a.n_chunks) return;
+  double* wsm = smem + (size_t)warp * MS::TOTAL;
+  double* wrec = wsm;                 // Ceres-layout rows of the current group of 8 blocks
+  double* stage = wsm + MS::STAGE;
+  double* own_x = wsm + MS::CONSTS;
+  double* ext_x = own_x + POSEX;
+  double* sh = ext_x + POSEX;
+  const Chunk ch = a.chunks[chunk_id];
+  const int b = lane >> 2, t = lane & 3;
+  const double* oth_table = OWN_IS_VIEW ? a.marker_x : a.view_x;
+  {
+    const double* src = (OWN_IS_VIEW ? a.view_x : a.marker_x) + (size_t)ch.own * POSEX;
+    if (lane < POSEX) own_x[lane] = src[lane];
+    if (RIG && lane < POSEX) ext_x[lane] = a.ext_x[(size_t)ch.cam * POSEX + lane];
+    if (lane < SP) sh[lane] = a.shared[ch.cam * SP + lane];
+  }
+  auto load_oth = [&](int it) -> int {
+    return (lane < BPW && it + lane < ch.count) ? a.oth[(int64_t)ch.start + it + lane] : 0;
+  };
+  auto load_pos = [&](int it) -> int {   // caller position of the lane's block
+    return (it + b < ch.count) ? (a.orig ? a.orig[(int64_t)ch.start + it + b] : ch.start + it + b) : 0;
+  };
+  auto issue_stage = [&](int it, int buf, int oth_reg) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {   // 8 records x 12 16-byte pieces
+      const int idx = lane + 32 * r;
+      const int q = idx / (POSEX / 2), c = idx - q * (POSEX / 2);
+      const int o = __shfl_sync(0xffffffffu, oth_reg, q);
+      if (it + q < ch.count)
+        ev_cp_async16(stage + (buf * BPW + q) * POSEX + 2 * c, oth_table + (size_t)o * POSEX + 2 * c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int oth_cur = load_oth(0);
+  int oth_nxt = load_oth(BPW);
+  issue_stage(0, 0, oth_cur);
+  int pos_nxt = load_pos(0);
+  double2 px_nxt = make_double2(0.0, 0.0);
+  if (b < ch.count) px_nxt = *reinterpret_cast<const double2*>(a.pix + ((int64_t)ch.start + b) * 8 + 2 * t);
+  double cost = 0.0;
+  int buf = 0;
+  for (int it = 0; it < ch.count; it += BPW, buf ^= 1) {
+    const bool valid = (it + b) < ch.count;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const double2 px = px_nxt;
+    const int pos = pos_nxt;
+    if (it + BPW < ch.count) {
+      issue_stage(it + BPW, buf ^ 1, oth_nxt);
+      oth_nxt = load_oth(it + 2 * BPW);
+      pos_nxt = load_pos(it + BPW);
+      if (it + BPW + b < ch.count)
+        px_nxt = *reinterpret_cast<const double2*>(a.pix + ((int64_t)ch.start + it + BPW + b) * 8 + 2 * t);
+    }
+    const double* ox_rec = stage + (buf * BPW + b) * POSEX;
+    const double* vx = OWN_IS_VIEW ? own_x : ox_rec;
+    const double* mx = OWN_IS_VIEW ? ox_rec : own_x;
+    BlockGeom<RIG> geo;
+    double ox = 0.0, oy = 0.0;
+    if (valid) {
+      block_geometry<RIG>(vx, mx, RIG ? ext_x : nullptr, geo);
+      corner_xy(t, mx[PX_HS], ox, oy);
+    }
+    // the previous group's bulk copies must have read the staging rows before they are rewritten
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    double r2 = 0.0;
+    if (valid) {
+      CeresSink<RIG, OWN_IS_VIEW> sink{wrec, b, t, {0, 0, 0, 0, 0}};
+      double r0, r1;
+      const double depth = eval_corner_emit<RIG>(geo, sh, ox, oy, px.x, px.y, sink, r0, r1);
+      if (!(depth > 0.0) || !isfinite(r0) || !isfinite(r1)) *a.fail_flag = 1;
+      r2 = r0 * r0 + r1 * r1;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the async proxy
+    __syncwarp();
+    // copy-out by the TMA engine: one bulk copy per output array when the group's blocks are
+    // consecutive in caller order, one per (block, array) otherwise
+    const int nblk = min(BPW, ch.count - it);
+    const int p0 = __shfl_sync(0xffffffffu, pos, 0);
+    const bool run = __all_sync(0xffffffffu, !valid || pos == p0 + b);
+    constexpr int NARR = RIG ? 6 : 5;
+    const int n_copies = run ? NARR : nblk * NARR;
+    for (int idx = lane; idx < ((n_copies + 31) & ~31); idx += 32) {   // uniform trip count: shuffle inside
+      const int qq = run ? 0 : idx / NARR, arr = run ? idx : idx - qq * NARR;
+      const int64_t o = __shfl_sync(0xffffffffu, pos, (qq & 7) * 4);
+      double* dst = nullptr;
+      int off = 0, k = 0;
+      switch (arr) {
+        case 0: dst = a.residuals; off = ER::RES; k = 8; break;
+        case 1: dst = a.jac_intr; off = ER::JI; k = 32; break;
+        case 2: dst = a.jac_dist; off = ER::JD; k = 40; break;
+        case 3: dst = a.jac_view; off = ER::JV; k = 48; break;
+        case 4: dst = a.jac_marker; off = ER::JM; k = 48; break;
+        default: dst = a.jac_ext; off = ER::JX; k = 48; break;
+      }
+      if (idx < n_copies && dst)
+        bulk_store(dst + o * k, wrec + off + qq * k, (run ? nblk : 1) * k * (int)sizeof(double));
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (a.loss != 0) {
+      double sb = r2 + __shfl_xor_sync(0xffffffffu, r2, 1);
+      sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+      double rho1;
+      r2 = valid ? 0.25 * robust_rho(a.loss, a.loss_a2, sb, rho1) : 0.0;
+    }
+    cost += r2;
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+  if (lane == 0 && a.cost2_partials) a.cost2_partials[chunk_id] = cost;
+}
+
+template <bool RIG, bool OWN_IS_VIEW>
+static void launch_materialise_t(const EvalArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)MAT_WARPS * MatSmem<RIG>::TOTAL * sizeof(double);
+  auto k = materialise_kernel<RIG, OWN_IS_VIEW>;
+  static bool attr = false;
+  if (!attr) {
+    RCC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  k<<<ceil_div(a.n_chunks, MAT_WARPS), MAT_WARPS * 32, smem, s>>>(a);
+  RCC_CUDA(cudaGetLastError());
+}
+
+int eval_partials(bool want_jac, const EvalArgs& a) { return want_jac ? a.n_chunks : eval_grid(a.n); }
+
 void launch_evaluate(bool rig, bool want_jac, const EvalArgs& a, cudaStream_t s) {
   if (a.n == 0) return;
-  if (rig) {
-    if (want_jac) launch_evaluate_t<true, true>(a, s);
-    else launch_evaluate_t<true, false>(a, s);
-  } else {
-    if (want_jac) launch_evaluate_t<false, true>(a, s);
-    else launch_evaluate_t<false, false>(a, s);
+  if (want_jac) {
+    if (rig) {
+      if (a.own_is_view) launch_materialise_t<true, true>(a, s);
+      else launch_materialise_t<true, false>(a, s);
+    } else {
+      if (a.own_is_view) launch_materialise_t<false, true>(a, s);
+      else launch_materialise_t<false, false>(a, s);
+    }
+    return;
   }
+  if (rig) launch_evaluate_t<true, false>(a, s);
+  else launch_evaluate_t<false, false>(a, s);
 }
 
 void launch_cost(bool rig, const EvalArgs& a, cudaStream_t s) {

@@ -136,9 +136,16 @@ struct EvalArgs {
   int32_t* fail_flag;
   int32_t loss;
   double loss_a2;
+  // chunk view of the same E-sorted blocks (materialising kernel: one warp per chunk)
+  const Chunk* chunks;
+  int32_t n_chunks;
+  const int32_t* oth;       // [n] other 6-dof block of each sorted block (own block comes from the chunk)
+  int32_t own_is_view;
 };
 int eval_grid(int64_t n);   // CTAs launch_evaluate / launch_cost will use
 void launch_evaluate(bool rig, bool want_jac, const EvalArgs& a, cudaStream_t s);
+// number of cost partials launch_evaluate writes (want_jac: one per chunk; else one per CTA)
+int eval_partials(bool want_jac, const EvalArgs& a);
 void launch_cost(bool rig, const EvalArgs& a, cudaStream_t s);
 // deterministic sum of n doubles -> out[0] (single CTA)
 void launch_sum(const double* in, int64_t n, double* out, double scale, cudaStream_t s);

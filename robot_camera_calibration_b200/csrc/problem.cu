@@ -338,7 +338,7 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
   P->part_f.alloc((size_t)P->n_chunks_f * (P->rig ? PassGeom<true>::PART_F : PassGeom<false>::PART_F));
   P->W.alloc((size_t)n * 36);
   P->Y.alloc((size_t)std::max<int64_t>(P->n_pairs, 1) * 36);
-  P->cost_partials.alloc((size_t)std::max(1, eval_grid(n)));
+  P->cost_partials.alloc((size_t)std::max(std::max(1, eval_grid(n)), P->n_chunks_e));
   RCC_CUDA(cudaStreamSynchronize(s));
   P->have_obs = true;
   P->linearized = P->schur_done = P->step_ready = P->cand_ready = false;
@@ -557,6 +557,10 @@ static EvalArgs eval_args(P_t* P, bool cand) {
   a.shared = cand ? P->shared_c.p : P->shared.p;
   a.sizes = P->sizes.p;
   a.cost2_partials = P->cost_partials.p;
+  a.chunks = P->e_chunks.p;
+  a.n_chunks = P->n_chunks_e;
+  a.oth = P->e_oth.p;
+  a.own_is_view = P->elim_view ? 1 : 0;
   a.fail_flag = P->fail_flag.p;
   a.loss = P->loss;
   a.loss_a2 = P->loss_scale * P->loss_scale;
@@ -1024,7 +1028,7 @@ static int evaluate_impl(P_t* P, int want_j, double* cost, bool to_host, double*
   {
     Scoped t(P, ST_EVALUATE, 2);
     launch_evaluate(P->rig, want_j != 0, a, P->stream);
-    launch_sum(P->cost_partials.p, eval_grid(P->n_obs), P->scalar.p, 0.5, P->stream);
+    launch_sum(P->cost_partials.p, eval_partials(want_j != 0, a), P->scalar.p, 0.5, P->stream);
   }
   int fail = 0;
   if (to_host) {
