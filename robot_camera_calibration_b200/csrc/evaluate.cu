@@ -1,17 +1,8 @@
 // K1 -- materialised cost-functor evaluation (residuals + per-parameter-block
-// Jacobians in the Ceres CostFunction::Evaluate layout), and K6's cost-only
-// evaluation used for the LM gain ratio.
+// Jacobians in the Ceres CostFunction::Evaluate layout: materialise_kernel), and
+// K6's cost-only evaluation used for the LM gain ratio (evaluate_kernel).
 //
-// One thread per tag corner (4 lanes = one observation block, a warp = a group
-// of 8 blocks); persistent warps walk the groups with the next group's indices
-// and pixels prefetched into registers.  The kernel is HBM-write-bound: 1 408 B
-// out per 72 B in.  A group's rows are staged in shared memory array-major
-// ([array][8 blocks][rows x cols], the Ceres layout of 8 consecutive residual
-// blocks) and leave the SM as TMA bulk copies (cp.async.bulk, SASS UBLKCP): one
-// copy of 0.5-3 KB per output array when the 8 blocks are consecutive in caller
-// order, one per (block, array) otherwise.  The copies of group i drain while
-// group i+1 is gathered and evaluated (wait_group.read sits right before the
-// staging buffer is written again).
+// K1 is HBM-write-bound: 1 408 B out per 72 B in per observation block.
 #include "common.cuh"
 #include "kernels.h"
 #include "model.cuh"
@@ -19,7 +10,7 @@
 namespace rcc {
 
 constexpr int EVAL_THREADS = 256;
-constexpr int EVAL_CTAS_PER_SM = 2;   // 128 registers x 256 threads; 91 KB staging per CTA
+constexpr int EVAL_CTAS_PER_SM = 2;   // 128 registers x 256 threads
 
 int eval_grid(int64_t n) {
   const int64_t groups = (n + 7) / 8;
@@ -61,16 +52,15 @@ struct EvalIdx {      // raw loads only: nothing here may wait on memory when th
   bool on;
 };
 
-template <bool RIG, bool WANT_J>
+// K6: residual / cost evaluation without Jacobians (LM gain ratio, Evaluate() without jacobians).
+// Persistent warps, a group of 8 blocks per warp iteration, the next group's indices and pixels in flight.
+template <bool RIG>
 __global__ void __launch_bounds__(EVAL_THREADS, EVAL_CTAS_PER_SM) evaluate_kernel(const EvalArgs a) {
-  using ER = EvalRec<RIG>;
   constexpr int SP = RIG ? 15 : 9;
   constexpr int WPC = EVAL_THREADS / 32;
   __shared__ double red[WPC];
-  extern __shared__ __align__(128) double stage[];   // WANT_J: [warps][ER::SIZE]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane >> 2, t = lane & 3;
-  double* wrec = WANT_J ? stage + (size_t)warp * ER::SIZE : nullptr;
   const int64_t n_groups = (a.n + 7) >> 3;
   const int64_t gw = (int64_t)blockIdx.x * WPC + warp, nw = (int64_t)gridDim.x * WPC;
   double cost = 0.0;
@@ -94,7 +84,6 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_CTAS_PER_SM) evaluate_kerne
   EvalIdx cur = load_idx(gw);
   for (int64_t grp = gw; grp < n_groups; grp += nw) {
     const EvalIdx nxt = load_idx(grp + nw);   // in flight during this group's arithmetic
-    CornerRows<RIG> c;
     double r2 = 0.0;
     if (cur.on) {
       // expanded pose records as 16-byte loads (the 4 corner lanes of a tag read the same lines)
@@ -121,78 +110,12 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_CTAS_PER_SM) evaluate_kerne
       block_geometry<RIG>(vx, mx, RIG ? xx : nullptr, geo);
       double ox, oy;
       corner_xy(t, mx[PX_HS], ox, oy);
-      eval_corner<RIG, WANT_J>(geo, a.shared + (size_t)cur.cam * SP, ox, oy, cur.px.x, cur.px.y, c);
+      CornerRows<RIG> c;
+      eval_corner<RIG, false>(geo, a.shared + (size_t)cur.cam * SP, ox, oy, cur.px.x, cur.px.y, c);
       if (!(c.depth > 0.0) || !isfinite(c.r[0]) || !isfinite(c.r[1])) *a.fail_flag = 1;
       r2 = c.r[0] * c.r[0] + c.r[1] * c.r[1];
-      if (!WANT_J && a.residuals)
+      if (a.residuals)
         *reinterpret_cast<double2*>(a.residuals + (int64_t)cur.o * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
-    }
-    if (WANT_J) {
-      // the previous group's bulk copies must have read the staging buffer before it is rewritten
-#ifndef RCC_K1_NOWAIT_EXPERIMENT
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#endif
-      __syncwarp();
-      if (cur.on) {
-        // stage the corner's two rows of every Jacobian block in Ceres layout
-        *reinterpret_cast<double2*>(wrec + ER::RES + q * 8 + 2 * t) = make_double2(c.r[0], c.r[1]);
-        double2* d = reinterpret_cast<double2*>(wrec + ER::JI + q * 32 + 8 * t);
-        d[0] = make_double2(c.js[0][0], c.js[0][1]);
-        d[1] = make_double2(c.js[0][2], c.js[0][3]);
-        d[2] = make_double2(c.js[1][0], c.js[1][1]);
-        d[3] = make_double2(c.js[1][2], c.js[1][3]);
-        d = reinterpret_cast<double2*>(wrec + ER::JD + q * 40 + 10 * t);
-        d[0] = make_double2(c.js[0][4], c.js[0][5]);
-        d[1] = make_double2(c.js[0][6], c.js[0][7]);
-        d[2] = make_double2(c.js[0][8], c.js[1][4]);
-        d[3] = make_double2(c.js[1][5], c.js[1][6]);
-        d[4] = make_double2(c.js[1][7], c.js[1][8]);
-        d = reinterpret_cast<double2*>(wrec + ER::JV + q * 48 + 12 * t);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jv[i][2 * j], c.jv[i][2 * j + 1]);
-        d = reinterpret_cast<double2*>(wrec + ER::JM + q * 48 + 12 * t);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jm[i][2 * j], c.jm[i][2 * j + 1]);
-        if (RIG) {
-          d = reinterpret_cast<double2*>(wrec + ER::JX + q * 48 + 12 * t);
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) d[3 * i + j] = make_double2(c.jx[i][2 * j], c.jx[i][2 * j + 1]);
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the async proxy
-      __syncwarp();
-      // hand the copy-out to the TMA engine
-      const int nblk = (int)min((int64_t)8, a.n - grp * 8);
-      const int o0 = __shfl_sync(0xffffffffu, cur.o, 0);
-      const bool run = __all_sync(0xffffffffu, !cur.on || cur.o == o0 + q);   // 8 consecutive caller positions
-      constexpr int NARR = RIG ? 6 : 5;
-      const int n_copies = run ? NARR : nblk * NARR;
-      for (int idx = lane; idx < ((n_copies + 31) & ~31); idx += 32) {   // uniform trip count: shuffles inside
-        const int qq = run ? 0 : idx / NARR, arr = run ? idx : idx - qq * NARR;
-        const int64_t o = __shfl_sync(0xffffffffu, cur.o, (qq & 7) * 4);
-        double* dst = nullptr;
-        int off = 0, k = 0;
-        switch (arr) {
-          case 0: dst = a.residuals; off = ER::RES; k = 8; break;
-          case 1: dst = a.jac_intr; off = ER::JI; k = 32; break;
-          case 2: dst = a.jac_dist; off = ER::JD; k = 40; break;
-          case 3: dst = a.jac_view; off = ER::JV; k = 48; break;
-          case 4: dst = a.jac_marker; off = ER::JM; k = 48; break;
-          default: dst = a.jac_ext; off = ER::JX; k = 48; break;
-        }
-#ifdef RCC_K1_EXPERIMENT_ARR
-        if (arr != RCC_K1_EXPERIMENT_ARR) dst = nullptr;   // timing experiment: only one output array is written
-#endif
-        if (idx < n_copies && dst)
-          bulk_store(dst + o * k, wrec + off + qq * k, (run ? nblk : 1) * k * (int)sizeof(double));
-      }
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (a.loss != 0) {
       // the 4 corner threads of a tag are adjacent lanes: rho(sum of the 8 squared residuals) / 4 each
@@ -204,23 +127,13 @@ __global__ void __launch_bounds__(EVAL_THREADS, EVAL_CTAS_PER_SM) evaluate_kerne
     cost += r2;
     cur = nxt;
   }
-  if (WANT_J) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
   const double s = block_sum(cost, red);
   if (threadIdx.x == 0 && a.cost2_partials) a.cost2_partials[blockIdx.x] = s;
 }
 
-template <bool RIG, bool WANT_J>
+template <bool RIG>
 static void launch_evaluate_t(const EvalArgs& a, cudaStream_t s) {
-  const int grid = eval_grid(a.n);
-  size_t smem = 0;
-  if (WANT_J) smem = (size_t)(EVAL_THREADS / 32) * EvalRec<RIG>::SIZE * sizeof(double);
-  auto k = evaluate_kernel<RIG, WANT_J>;
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    RCC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  k<<<grid, EVAL_THREADS, smem, s>>>(a);
+  evaluate_kernel<RIG><<<eval_grid(a.n), EVAL_THREADS, 0, s>>>(a);
   RCC_CUDA(cudaGetLastError());
 }
 
@@ -427,8 +340,8 @@ void launch_evaluate(bool rig, bool want_jac, const EvalArgs& a, cudaStream_t s)
     }
     return;
   }
-  if (rig) launch_evaluate_t<true, false>(a, s);
-  else launch_evaluate_t<false, false>(a, s);
+  if (rig) launch_evaluate_t<true>(a, s);
+  else launch_evaluate_t<false>(a, s);
 }
 
 void launch_cost(bool rig, const EvalArgs& a, cudaStream_t s) {

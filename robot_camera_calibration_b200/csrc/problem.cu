@@ -88,6 +88,10 @@ rcc_ba_problem::~rcc_ba_problem() {
   if (comm) ncclCommDestroy(comm);
   if (solver) cusolverDnDestroy(solver);
   if (h_pinned) cudaFreeHost(h_pinned);
+  for (auto& hs : hslot) {
+    if (hs.p) cudaFreeHost(hs.p);
+    if (hs.ev) cudaEventDestroy(hs.ev);
+  }
   if (own_stream && stream) cudaStreamDestroy(stream);
   if (side_stream) cudaStreamDestroy(side_stream);
   if (ev_fork) cudaEventDestroy(ev_fork);
@@ -109,6 +113,29 @@ typedef rcc_ba_problem P_t;
   } while (0)
 
 static void sync(P_t* P) { RCC_CUDA(cudaStreamSynchronize(P->stream)); }
+
+// caller buffer -> internal pinned slot (waits for the slot's previous H2D copy, normally long done)
+enum { HS_VIEWS = 0, HS_MARKERS, HS_INTR, HS_DIST, HS_EXT };
+static void* stage_in(P_t* P, int slot, const void* src, size_t bytes) {
+  auto& hs = P->hslot[slot];
+  if (hs.busy) {
+    RCC_CUDA(cudaEventSynchronize(hs.ev));
+    hs.busy = false;
+  }
+  if (bytes > hs.cap) {
+    if (hs.p) RCC_CUDA(cudaFreeHost(hs.p));
+    hs.p = nullptr;
+    RCC_CUDA(cudaMallocHost(&hs.p, bytes));
+    hs.cap = bytes;
+  }
+  if (!hs.ev) RCC_CUDA(cudaEventCreateWithFlags(&hs.ev, cudaEventDisableTiming));
+  memcpy(hs.p, src, bytes);
+  return hs.p;
+}
+static void stage_issued(P_t* P, int slot) {
+  RCC_CUDA(cudaEventRecord(P->hslot[slot].ev, P->stream));
+  P->hslot[slot].busy = true;
+}
 
 static double* x_e(P_t* P, bool cand = false) {
   return P->elim_view ? (cand ? P->views_c.p : P->views.p) : (cand ? P->markers_c.p : P->markers.p);
@@ -863,15 +890,16 @@ static void invalidate(P_t* P) {
 int rcc_ba_set_intrinsics(rcc_ba_problem* P, const double* intr, const double* dist) {
   API_BEGIN(P)
   RCC_REQUIRE(intr && dist, RCC_BAD_ARG, "null pointer");
-  std::vector<double> h((size_t)P->n_shared);
-  P->shared.download(h.data(), h.size(), P->stream);
-  sync(P);
-  for (int c = 0; c < P->n_cam; ++c) {
-    for (int k = 0; k < 4; ++k) h[(size_t)c * P->sp + k] = intr[c * 4 + k];
-    for (int k = 0; k < 5; ++k) h[(size_t)c * P->sp + 4 + k] = dist[c * 5 + k];
-  }
-  P->shared.upload(h, P->stream);
-  sync(P);
+  // strided scatter into the per-camera records [fx fy cx cy | k1 k2 p1 p2 k3 | ext]: no read-modify-write, no sync
+  const size_t pitch = (size_t)P->sp * sizeof(double);
+  const void* hi = stage_in(P, HS_INTR, intr, (size_t)P->n_cam * 4 * sizeof(double));
+  RCC_CUDA(cudaMemcpy2DAsync(P->shared.p, pitch, hi, 4 * sizeof(double), 4 * sizeof(double), P->n_cam,
+                             cudaMemcpyHostToDevice, P->stream));
+  stage_issued(P, HS_INTR);
+  const void* hd = stage_in(P, HS_DIST, dist, (size_t)P->n_cam * 5 * sizeof(double));
+  RCC_CUDA(cudaMemcpy2DAsync(P->shared.p + 4, pitch, hd, 5 * sizeof(double), 5 * sizeof(double), P->n_cam,
+                             cudaMemcpyHostToDevice, P->stream));
+  stage_issued(P, HS_DIST);
   invalidate(P);
   API_END(P)
 }
@@ -880,13 +908,10 @@ int rcc_ba_set_rig_extrinsics(rcc_ba_problem* P, const double* ext) {
   API_BEGIN(P)
   RCC_REQUIRE(ext, RCC_BAD_ARG, "null pointer");
   RCC_REQUIRE(P->rig, RCC_BAD_ARG, "extrinsics exist only in the rig model");
-  std::vector<double> h((size_t)P->n_shared);
-  P->shared.download(h.data(), h.size(), P->stream);
-  sync(P);
-  for (int c = 0; c < P->n_cam; ++c)
-    for (int k = 0; k < 6; ++k) h[(size_t)c * P->sp + 9 + k] = ext[c * 6 + k];
-  P->shared.upload(h, P->stream);
-  sync(P);
+  const void* he = stage_in(P, HS_EXT, ext, (size_t)P->n_cam * 6 * sizeof(double));
+  RCC_CUDA(cudaMemcpy2DAsync(P->shared.p + 9, (size_t)P->sp * sizeof(double), he, 6 * sizeof(double), 6 * sizeof(double),
+                             P->n_cam, cudaMemcpyHostToDevice, P->stream));
+  stage_issued(P, HS_EXT);
   invalidate(P);
   API_END(P)
 }
@@ -895,8 +920,9 @@ int rcc_ba_set_view_poses(rcc_ba_problem* P, const double* views) {
   API_BEGIN(P)
   RCC_REQUIRE(views, RCC_BAD_ARG, "null pointer");
   Scoped t(P, ST_H2D, 0);
-  P->views.upload(views, (size_t)P->n_views * 6, P->stream);
-  sync(P);
+  const size_t bytes = (size_t)P->n_views * 6 * sizeof(double);
+  RCC_CUDA(cudaMemcpyAsync(P->views.p, stage_in(P, HS_VIEWS, views, bytes), bytes, cudaMemcpyHostToDevice, P->stream));
+  stage_issued(P, HS_VIEWS);
   invalidate(P);
   API_END(P)
 }
@@ -905,8 +931,10 @@ int rcc_ba_set_marker_poses(rcc_ba_problem* P, const double* markers) {
   API_BEGIN(P)
   RCC_REQUIRE(markers, RCC_BAD_ARG, "null pointer");
   Scoped t(P, ST_H2D, 0);
-  P->markers.upload(markers, (size_t)P->n_markers * 6, P->stream);
-  sync(P);
+  const size_t bytes = (size_t)P->n_markers * 6 * sizeof(double);
+  RCC_CUDA(cudaMemcpyAsync(P->markers.p, stage_in(P, HS_MARKERS, markers, bytes), bytes, cudaMemcpyHostToDevice,
+                           P->stream));
+  stage_issued(P, HS_MARKERS);
   invalidate(P);
   API_END(P)
 }

@@ -96,6 +96,10 @@ struct rcc_ba_problem {
 
   // pinned host scratch for small read-backs
   double* h_pinned = nullptr;
+  // pinned staging slots for parameter uploads: the setters copy the caller's buffer here and return
+  // without a stream synchronisation; a slot is reused only after its previous H2D copy has completed
+  struct HostSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool busy = false; };
+  HostSlot hslot[5];
 
   ~rcc_ba_problem();
 };
