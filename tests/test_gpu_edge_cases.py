@@ -161,3 +161,26 @@ def test_deterministic_bitwise_repeatability():
         res.append((S, b, nb["Hee"], nb["Hss"]))
     for a, b in zip(*res):
         assert np.array_equal(a, b)                             # fixed summation order, no atomics
+
+
+@pytest.mark.parametrize("model", ["single", "rig"])
+@pytest.mark.parametrize("elim", ["views", "markers"])
+def test_evaluate_in_shuffled_caller_order(model, elim):
+    """Evaluate() must return residual blocks in the caller's order whatever the internal sort is:
+    a random caller order exercises the per-(block, array) copy-out of the materialising kernel,
+    the view-major order of make_scene its one-copy-per-array path."""
+    kw = dict(n_cam=2, model="rig") if model == "rig" else {}
+    s = make_scene(14, 23, 0.8, seed=57, **kw)
+    perm = np.random.default_rng(5).permutation(s.n_blocks)
+    s.view_idx, s.marker_idx, s.cam_idx, s.pixels = s.view_idx[perm], s.marker_idx[perm], s.cam_idx[perm], s.pixels[perm]
+    p = to_oracle(s)
+    r, Jb = O.residuals(p), O.jacobian_blocks_cs(p)
+    with BAProblem.from_scene(s, eliminate=elim) as gp:
+        out = gp.evaluate()
+        res_only = gp.evaluate(want_jacobians=False)
+    assert abs(out["cost"] - O.cost(p)) <= TOL * O.cost(p)
+    assert abs(res_only["cost"] - O.cost(p)) <= TOL * O.cost(p)
+    assert max_block_rel(out["residuals"], r) < TOL
+    assert max_block_rel(res_only["residuals"], r) < TOL
+    for k in Jb:
+        assert max_block_rel(out["jacobians"][k], Jb[k]) < TOL, k
