@@ -100,7 +100,9 @@ const char* rcc_ba_version(void);
 /* use the caller's CUDA stream (a cudaStream_t cast to void*) instead of the handle's own */
 int rcc_ba_set_stream(rcc_ba_problem* p, void* cuda_stream);
 
-/* ---- problem setup (host AoS in, Ceres-style contiguous double[k] blocks) ---- */
+/* ---- problem setup (host AoS in, Ceres-style contiguous double[k] blocks) ----
+ * The parameter setters copy the caller's array into an internal pinned slot and return without a stream
+ * synchronisation: the array may be reused as soon as the call returns. */
 int rcc_ba_set_intrinsics(rcc_ba_problem* p, const double* intr /*n_cam x 4*/, const double* dist /*n_cam x 5*/);
 int rcc_ba_set_rig_extrinsics(rcc_ba_problem* p, const double* ext /*n_cam x 6*/);
 int rcc_ba_set_view_poses(rcc_ba_problem* p, const double* views /*n_views x 6*/);
@@ -110,8 +112,12 @@ int rcc_ba_set_marker_sizes(rcc_ba_problem* p, const double* sizes /*n_markers*/
  * by eliminated-block owner and builds the segment / chunk / Schur index tables. */
 int rcc_ba_set_observations(rcc_ba_problem* p, const int32_t* view_idx, const int32_t* marker_idx,
                             const int32_t* cam_idx, const double* pixels);
-/* replace the pixel coordinates only (same indices, caller order): one H2D copy plus a
- * device-side permutation into the sorted layouts */
+/* replace the pixel coordinates only (same indices, caller order).  Asynchronous: `pixels` must stay
+ * valid until the next call that returns results (linearize with a cost pointer, evaluate, any getter).
+ * When the caller order is the sorted order (blocks listed per eliminated block) the copy runs on a side
+ * stream in 4 pieces and the next rcc_ba_linearize starts the E pass of a piece as soon as it has landed:
+ * call the parameter setters BEFORE update_pixels so that they do not queue behind it.  Otherwise: one
+ * H2D copy plus a device-side permutation into the sorted layouts. */
 int rcc_ba_update_pixels(rcc_ba_problem* p, const double* pixels /*n_obs_blocks x 8*/);
 /* hold a parameter block constant (the gauge: world tag, camera_pose.cpp:71-80) */
 int rcc_ba_set_constant(rcc_ba_problem* p, int32_t block_kind, int32_t index, int32_t is_constant);

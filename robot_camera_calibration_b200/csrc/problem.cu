@@ -96,6 +96,8 @@ rcc_ba_problem::~rcc_ba_problem() {
   if (side_stream) cudaStreamDestroy(side_stream);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
+  for (auto e : ev_piece)
+    if (e) cudaEventDestroy(e);
 }
 
 typedef rcc_ba_problem P_t;
@@ -206,6 +208,8 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
                           const double* pixels) {
   const int64_t n = P->n_obs;
   RCC_REQUIRE(n < (int64_t)2000000000 / 36 * 8, RCC_BAD_ARG, "too many observation blocks for 32-bit indexing");
+  RCC_CUDA(cudaStreamSynchronize(P->side_stream));   // a piecewise pixel upload may still target the old buffers
+  P->pix_pending = false;
   std::vector<int32_t> cam_zero;
   if (!cam_idx) {
     cam_zero.assign((size_t)n, 0);
@@ -251,6 +255,23 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
     P->e_orig.upload(perm_e, s);
     P->e_pix.upload(pix, s);
     RCC_CUDA(cudaStreamSynchronize(s));
+  }
+  {
+    // caller order == E-sorted order (observations listed per eliminated block, the usual case):
+    // update_pixels can then copy straight into e_pix, piece by piece, cut at chunk boundaries
+    bool ident = true;
+    for (int64_t i = 0; i < n && ident; ++i) ident = perm_e[i] == (int32_t)i;
+    P->pix_identity = ident && n > 0;
+    P->pix_pending = false;
+    const int nc = P->n_chunks_e;
+    P->piece_chunk[0] = 0;
+    P->piece_block[0] = 0;
+    for (int k = 1; k <= rcc_ba_problem::PIX_PIECES; ++k) {
+      int c = (int)((int64_t)nc * k / rcc_ba_problem::PIX_PIECES);
+      c = std::max(c, P->piece_chunk[k - 1]);
+      P->piece_chunk[k] = (k == rcc_ba_problem::PIX_PIECES) ? nc : c;
+      P->piece_block[k] = (P->piece_chunk[k] >= nc) ? n : (int64_t)chunks[P->piece_chunk[k]].start;
+    }
   }
   {
     std::vector<int32_t> cnt((size_t)P->n_e);
@@ -404,6 +425,15 @@ static void ensure_expanded(P_t* P) {
   P->expanded_valid = true;
 }
 
+// after a piecewise update_pixels: wait for the last piece and bring f_pix up to date
+static void ensure_pixels(P_t* P) {
+  if (!P->pix_pending) return;
+  RCC_CUDA(cudaStreamWaitEvent(P->stream, P->ev_piece[rcc_ba_problem::PIX_PIECES - 1], 0));
+  launch_permute_pixels(P->e_pix.p, P->f_orig.p, P->f_pix.p, P->n_obs, P->stream);
+  P->launch_count += 1;
+  P->pix_pending = false;
+}
+
 static void do_linearize(P_t* P) {
   RCC_REQUIRE(P->have_obs, RCC_NOT_READY, "set_observations has not been called");
   ensure_expanded(P);
@@ -425,8 +455,26 @@ static void do_linearize(P_t* P) {
     a.n_chunks = P->n_chunks_e;
     a.partials = P->part_e.p;
     a.W = P->W.p;
-    launch_assemble(P->rig, true, P->elim_view, a, P->stream);
+    if (P->pix_pending) {
+      // pixels are still arriving on the side stream: the E pass of a piece starts when the piece has landed
+      const int part = P->rig ? PassGeom<true>::PART_E : PassGeom<false>::PART_E;
+      for (int k = 0; k < rcc_ba_problem::PIX_PIECES; ++k) {
+        const int c0 = P->piece_chunk[k], c1 = P->piece_chunk[k + 1];
+        RCC_CUDA(cudaStreamWaitEvent(P->stream, P->ev_piece[k], 0));
+        if (c1 <= c0) continue;
+        AssembleArgs ak = a;
+        ak.chunks = P->e_chunks.p + c0;
+        ak.n_chunks = c1 - c0;
+        ak.partials = P->part_e.p + (size_t)c0 * part;
+        launch_assemble(P->rig, true, P->elim_view, ak, P->stream);
+        P->launch_count += 1;
+      }
+      P->launch_count -= 1;   // Scoped already counted one E-pass launch
+    } else {
+      launch_assemble(P->rig, true, P->elim_view, a, P->stream);
+    }
   }
+  ensure_pixels(P);
   {
     Scoped t(P, ST_ASSEMBLE_F, 1);
     a.oth = P->f_oth.p;
@@ -596,6 +644,7 @@ static EvalArgs eval_args(P_t* P, bool cand) {
 
 static void do_candidate_cost(P_t* P) {
   RCC_REQUIRE(P->step_ready, RCC_NOT_READY, "solve_step has not been called");
+  ensure_pixels(P);
   {
     Scoped t(P, ST_EXPAND, 1);
     launch_expand_poses(P->views_c.p, P->n_views, P->view_xc.p, P->markers_c.p, P->sizes.p, P->n_markers, P->marker_xc.p,
@@ -819,6 +868,7 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     RCC_CUDA(cudaStreamCreateWithFlags(&P->side_stream, cudaStreamNonBlocking));
     RCC_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
     RCC_CUDA(cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming));
+    for (auto& e : P->ev_piece) RCC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     RCC_CUDA(cudaMallocHost(&P->h_pinned, 64 * sizeof(double)));
     cudaStream_t s = P->stream;
     P->views.alloc((size_t)P->n_views * 6); P->views.zero(s);
@@ -867,6 +917,7 @@ void rcc_ba_destroy(rcc_ba_problem* p) {
   if (!p) return;
   cudaSetDevice(p->opt.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->side_stream) cudaStreamSynchronize(p->side_stream);
   delete p;
 }
 
@@ -960,7 +1011,21 @@ int rcc_ba_update_pixels(rcc_ba_problem* P, const double* pixels) {
   API_BEGIN(P)
   RCC_REQUIRE(pixels, RCC_BAD_ARG, "null pointer");
   RCC_REQUIRE(P->have_obs, RCC_NOT_READY, "set_observations has not been called");
-  {
+  if (P->pix_identity) {
+    // caller order is the E-sorted order: copy straight into e_pix on the side stream, in pieces cut at
+    // chunk boundaries; linearize overlaps its E pass with the pieces still in flight
+    Scoped t(P, ST_H2D, 0);
+    RCC_CUDA(cudaEventRecord(P->ev_fork, P->stream));          // earlier readers of e_pix on the main stream
+    RCC_CUDA(cudaStreamWaitEvent(P->side_stream, P->ev_fork, 0));
+    for (int k = 0; k < rcc_ba_problem::PIX_PIECES; ++k) {
+      const int64_t b0 = P->piece_block[k], b1 = P->piece_block[k + 1];
+      if (b1 > b0)
+        RCC_CUDA(cudaMemcpyAsync(P->e_pix.p + b0 * 8, pixels + b0 * 8, (size_t)(b1 - b0) * 8 * sizeof(double),
+                                 cudaMemcpyHostToDevice, P->side_stream));
+      RCC_CUDA(cudaEventRecord(P->ev_piece[k], P->side_stream));
+    }
+    P->pix_pending = true;
+  } else {
     Scoped t(P, ST_H2D, 2);
     P->pix_staging.upload(pixels, (size_t)P->n_obs * 8, P->stream);
     launch_permute_pixels(P->pix_staging.p, P->e_orig.p, P->e_pix.p, P->n_obs, P->stream);
@@ -1041,6 +1106,7 @@ static int evaluate_impl(P_t* P, int want_j, double* cost, bool to_host, double*
                          double* jv, double* jm, double* jx) {
   RCC_REQUIRE(P->have_obs, RCC_NOT_READY, "set_observations has not been called");
   ensure_expanded(P);
+  ensure_pixels(P);
   const size_t n = (size_t)P->n_obs;
   EvalArgs a = eval_args(P, false);
   const bool all = !to_host;  // device mode materialises everything

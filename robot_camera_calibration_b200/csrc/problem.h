@@ -51,6 +51,15 @@ struct rcc_ba_problem {
   // fork/join side stream: small kernels that only depend on the previous stage run beside the big one
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // piecewise pixel upload (rcc_ba_update_pixels when the caller order is the E-sorted order): the H2D
+  // copy runs on the side stream in PIX_PIECES pieces cut at chunk boundaries, and the next linearize
+  // starts the E pass of a piece as soon as that piece has landed
+  static constexpr int PIX_PIECES = 4;
+  bool pix_identity = false;         // e_orig is the identity permutation
+  bool pix_pending = false;          // pieces in flight; f_pix not yet permuted
+  int piece_chunk[PIX_PIECES + 1] = {0};
+  int64_t piece_block[PIX_PIECES + 1] = {0};
+  cudaEvent_t ev_piece[PIX_PIECES] = {nullptr};
   std::string err;
   int64_t launch_count = 0;
 

@@ -184,3 +184,39 @@ def test_evaluate_in_shuffled_caller_order(model, elim):
     assert max_block_rel(res_only["residuals"], r) < TOL
     for k in Jb:
         assert max_block_rel(out["jacobians"][k], Jb[k]) < TOL, k
+
+
+@pytest.mark.parametrize("shuffled", [False, True])
+def test_update_pixels_matches_a_fresh_problem(shuffled):
+    """rcc_ba_update_pixels: new pixel coordinates on the same indices must give exactly what a problem
+    built from those pixels gives -- in the caller order == sorted order case (piecewise upload on the side
+    stream, overlapped with the E pass) and in the general case (staging buffer + device permutation),
+    followed by linearize, by evaluate, and twice in a row."""
+    s = make_scene(60, 40, 0.7, seed=58)
+    if shuffled:
+        perm = np.random.default_rng(6).permutation(s.n_blocks)
+        s.view_idx, s.marker_idx, s.cam_idx, s.pixels = s.view_idx[perm], s.marker_idx[perm], s.cam_idx[perm], s.pixels[perm]
+    rng = np.random.default_rng(7)
+    pix2 = np.ascontiguousarray(s.pixels + rng.normal(0.0, 0.5, s.pixels.shape))
+    pix3 = np.ascontiguousarray(s.pixels + rng.normal(0.0, 0.5, s.pixels.shape))
+    with BAProblem.from_scene(s) as gp:
+        gp.linearize()
+        gp.update_pixels(pix2)
+        c2 = gp.linearize()
+        nb2 = gp.normal_blocks()
+        gp.update_pixels(pix3)
+        gp.update_pixels(pix2)                       # overwritten before anything consumed it
+        e2 = gp.evaluate(want_jacobians=False)
+        gp.update_pixels(pix3)
+        c3 = gp.linearize()
+    ref = make_scene(60, 40, 0.7, seed=58)
+    ref.view_idx, ref.marker_idx, ref.cam_idx = s.view_idx, s.marker_idx, s.cam_idx
+    for pix, cost, nb in ((pix2, c2, nb2), (pix3, c3, None)):
+        ref.pixels = pix
+        with BAProblem.from_scene(ref) as gq:
+            assert gq.linearize() == cost
+            if nb is not None:
+                nq = gq.normal_blocks()
+                for k in ("Hee", "Hff", "W", "ge", "gf", "Hes", "Hfs", "Hss", "gs"):
+                    assert np.array_equal(nq[k], nb[k]), k
+                assert np.array_equal(gq.evaluate(want_jacobians=False)["residuals"], e2["residuals"])
