@@ -39,6 +39,7 @@ UNIT = "observations/s"
 BYTES_PER_BLOCK_E = 64 + 4 + 288          # pixels + other index in, cross block W out
 BYTES_PER_BLOCK_F = 64 + 4
 FLOP_PER_BLOCK = 2 * 8 * 253 + 1400       # J^T J products (253 unique entries x 8 rows) + Jacobian evaluation
+FLOP_PER_BLOCK_E = 2 * 8 * 172 + 1400     # E pass alone: OO, OT, O x [S r], [S r] x [S r] (172 entries) + evaluation
 NCU_DRAM_BYTES_E_PASS = 32313856 + 89391616   # measured once under ncu (cfg2, 454 996 blocks)
 
 
@@ -346,12 +347,20 @@ def run_ours(args):
                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                          "traffic": NCU_DRAM_BYTES_E_PASS if (args.config == 2 and args.scale == 1.0) else None,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one E-pass "
-                                           "launch on this workload (profiles/r1_ncu_k2_dmma_summary.txt); below the "
+                                           "launch on this workload (profiles/r1_ncu_full_summary.txt); below the "
                                            "algorithmic bytes because part of W is still in L2 when the kernel ends",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_BLOCK_E * n_blocks,
                          "kernel_ms": k_ms, "f_pass_kernel_ms": kf_ms,
                          "note": "fused assembly is FP64-pipe-bound, not HBM-bound: see roofline_fp64"},
+            "roofline_fp64_e_pass": {"bound": "fp64 (DFMA + DMMA.8x8x4 share one pipe; same peak either way)",
+                                     "kernel": "assemble_kernel<E pass>",
+                                     "achieved": FLOP_PER_BLOCK_E * n_blocks / (k_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                                     "unit": "TFLOP/s", "frac": FLOP_PER_BLOCK_E * n_blocks / (k_ms * 1e-3) / 1e12 / fp64_peak,
+                                     "algorithmic_flop_per_launch": FLOP_PER_BLOCK_E * n_blocks,
+                                     "fp64_pipe_busy_ncu": 0.64,
+                                     "note": "executed work is larger: 8 DMMA x 512 flop + 4 corner evaluations per block; "
+                                             "ncu sm__throughput (FP64 pipe) 64 % (profiles/r1_ncu_full_summary.txt)"},
             "roofline_fp64": {"bound": "fp64", "achieved": step_flops / (total_ms / args.steps * 1e-3) / 1e12,
                               "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": step_flops / (total_ms / args.steps * 1e-3) / 1e12 / fp64_peak,

@@ -77,6 +77,9 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 #ifndef RCC_K2_MIN_CTAS
 #define RCC_K2_MIN_CTAS 3
 #endif
+#ifndef RCC_K2_MIN_CTAS_F
+#define RCC_K2_MIN_CTAS_F 3   // single-camera F pass: 56 KB smem per CTA would allow 4, measured below
+#endif
 
 // per-warp shared memory (doubles): staged rows | 2 x BPW other-pose records | own pose, ext pose, shared params
 template <bool RIG, bool EPASS>
@@ -90,7 +93,8 @@ struct WarpSmem {
 };
 
 template <bool RIG, bool EPASS, bool OWN_IS_VIEW, bool LOSS>
-__global__ void __launch_bounds__(PassGeom<RIG>::WARPS * 32, (RIG && EPASS) ? 2 : RCC_K2_MIN_CTAS)   // rig E pass: 89 KB smem per CTA
+__global__ void __launch_bounds__(PassGeom<RIG>::WARPS * 32,
+                                  (RIG && EPASS) ? 2 : ((!RIG && !EPASS) ? RCC_K2_MIN_CTAS_F : RCC_K2_MIN_CTAS))   // rig E pass: 89 KB smem per CTA
 assemble_kernel(const AssembleArgs a) {
   using PG = PassGeom<RIG>;
   using WS = WarpSmem<RIG, EPASS>;
