@@ -375,12 +375,18 @@ __device__ __forceinline__ void finalize_shared_partial_body(const FinalizeShare
   double acc[NR];
 #pragma unroll
   for (int j = 0; j < NR; ++j) acc[j] = 0.0;
-#pragma unroll 2
-  for (int c = lo + warp; c < hi; c += 8) {
-    const double* src = part + (size_t)list[c] * PART;
+  // chunk ids of the warp first (one load per lane), so that the partial loads below do not wait on them
+  for (int c0 = lo + warp; c0 < hi; c0 += 8 * 32) {
+    const int cmine = c0 + 8 * lane;
+    const int id_lane = (cmine < hi) ? list[cmine] : 0;
+    const int cnt = min(32, (hi - c0 + 7) / 8);
+#pragma unroll 4
+    for (int i = 0; i < cnt; ++i) {
+      const double* src = part + (size_t)__shfl_sync(0xffffffffu, id_lane, i) * PART;
 #pragma unroll
-    for (int j = 0; j < NR; ++j)
-      if (lane + 32 * j < PART) acc[j] += src[lane + 32 * j];
+      for (int j = 0; j < NR; ++j)
+        if (lane + 32 * j < PART) acc[j] += src[lane + 32 * j];
+    }
   }
 #pragma unroll
   for (int j = 0; j < NR; ++j)
@@ -414,8 +420,11 @@ __device__ __forceinline__ int shared_src(int i, int j) {
 }
 
 template <bool RIG>
-__global__ void __launch_bounds__(256) finalize_shared_final_kernel(const FinalizeSharedArgs a) {
+__global__ void __launch_bounds__(1024) finalize_shared_final_kernel(const FinalizeSharedArgs a) {
   constexpr int SP = PassGeom<RIG>::SP, PART = PassGeom<RIG>::PART_E;
+  constexpr int NQ = 4, SPQ = FIN_SLICES / NQ;       // 4 thread groups sum 16 slices each, then are added in order
+  static_assert(FIN_SLICES % NQ == 0 && PART <= 1024 / NQ * 2, "finalize_shared_final geometry");
+  __shared__ double red[NQ][PART];
   __shared__ double tot[PART];
   const int cam = blockIdx.x;
   const int tid = threadIdx.x;
@@ -423,10 +432,20 @@ __global__ void __launch_bounds__(256) finalize_shared_final_kernel(const Finali
   double* H = a.Hss;
   const int base = cam * SP;
   for (int k = tid; k < SP * ns; k += blockDim.x) H[(size_t)base * ns + k] = 0.0;
+  {
+    const int q = tid / 256;
+    for (int k = tid - 256 * q; k < PART; k += 256) {
+      double s = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < SPQ; ++sl) s += a.scratch[((size_t)cam * FIN_SLICES + q * SPQ + sl) * PART + k];
+      red[q][k] = s;
+    }
+  }
+  __syncthreads();
   for (int k = tid; k < PART; k += blockDim.x) {
     double s = 0.0;
-#pragma unroll 16
-    for (int sl = 0; sl < FIN_SLICES; ++sl) s += a.scratch[((size_t)cam * FIN_SLICES + sl) * PART + k];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) s += red[q][k];
     tot[k] = s;
   }
   __syncthreads();
@@ -465,10 +484,10 @@ void launch_finalize(bool rig, const FinalizeSideArgs& e, const FinalizeSideArgs
   const int grid = e.n_own + f.n_own + FIN_SLICES * sh.n_cam;
   if (rig) {
     finalize_fused_kernel<true><<<grid, 256, 0, s>>>(e, f, sh);
-    finalize_shared_final_kernel<true><<<sh.n_cam, 256, 0, s>>>(sh);
+    finalize_shared_final_kernel<true><<<sh.n_cam, 1024, 0, s>>>(sh);
   } else {
     finalize_fused_kernel<false><<<grid, 256, 0, s>>>(e, f, sh);
-    finalize_shared_final_kernel<false><<<sh.n_cam, 256, 0, s>>>(sh);
+    finalize_shared_final_kernel<false><<<sh.n_cam, 1024, 0, s>>>(sh);
   }
   RCC_CUDA(cudaGetLastError());
 }

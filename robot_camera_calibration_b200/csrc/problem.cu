@@ -863,6 +863,8 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     P->n_red = 6 * P->n_f + P->n_shared;
     P->ld = 6 * P->n_f + 6 * P->n_bb;
     RCC_REQUIRE((int64_t)P->n_red * P->ld < (int64_t)1 << 40, RCC_BAD_ARG, "reduced system too large");
+    RCC_REQUIRE(P->n_bb * 6 <= 128, RCC_BAD_ARG,
+                "too many cameras: the shared border holds at most 125 parameters (8 rig or 13 single-model cameras)");
     RCC_CUDA(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     P->own_stream = true;
     RCC_CUDA(cudaStreamCreateWithFlags(&P->side_stream, cudaStreamNonBlocking));

@@ -133,6 +133,9 @@ def test_argument_and_call_order_errors():
         with pytest.raises(L.RccError) as e:
             gp.reduced_system()
         assert e.value.status == L.RCC_NOT_READY
+    with pytest.raises(L.RccError) as e:            # 14 single-model cameras = 126 shared parameters: over the border limit
+        BAProblem(4, 4, 14, 8)
+    assert e.value.status == L.RCC_BAD_ARG and "cameras" in str(e.value)
 
 
 def test_constant_intrinsics_and_all_views_constant():
