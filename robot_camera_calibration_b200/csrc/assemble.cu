@@ -297,69 +297,82 @@ void launch_assemble(bool rig, bool epass, bool own_is_view, const AssembleArgs&
 }
 
 // ---------------------------------------------------------------------------
-// finalize_side: one CTA per own block sums its chunk partials in chunk order.
-// thread (r, j): row r of the own block; j < 6 -> H_oo[r][j], j == 6 -> g_o[r],
+// finalize_side: one warp per own block sums its chunk partials in chunk order.
+// output (r, j): row r of the own block; j < 6 -> H_oo[r][j], j == 6 -> g_o[r],
 // j >= 7 -> H_os[r][shared parameter j - 7] (kept per camera).
 // ---------------------------------------------------------------------------
 template <bool RIG, bool EPASS>
 __device__ __forceinline__ void finalize_side_body(const FinalizeSideArgs& a, int i) {
+  // one WARP per own block i; lane l sums outputs l, l + 32, ... over the block's chunks in chunk order
   using PG = PassGeom<RIG>;
   constexpr int SP = PG::SP, NJ = 7 + SP;
   constexpr int PART = EPASS ? PG::PART_E : PG::PART_F;
   constexpr int T_AX = EPASS ? (int)TE_AX : (int)TF_AX;
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (i >= a.n_own) return;
   double* hos = a.Hos + (size_t)i * 6 * a.n_shared;
-  for (int k = tid; k < 6 * a.n_shared; k += blockDim.x) hos[k] = 0.0;
-  __syncthreads();
-  if (tid >= 6 * NJ) return;
-  const int r = tid / NJ, j = tid - r * NJ;
-  // element of the chunk partial this thread sums
-  int src;
-  if (j < 6) src = TE_AA * 64 + r * 8 + j;
-  else if (j == 6) src = TE_AB * 64 + r * 8 + 7;
-  else if (j < 9) src = TE_AA * 64 + r * 8 + (j - 1);       // fx fy: columns 6, 7 of tile A
-  else if (j < 16) src = TE_AB * 64 + r * 8 + (j - 9);      // cx .. k3: columns 0..6 of tile B
-  else src = T_AX * 64 + r * 8 + (j - 16);                  // rig extrinsics
   const int c0 = a.chunk_ptr[i], c1 = a.chunk_ptr[i + 1];
-  const double* __restrict__ part = a.partials + src;
   const Chunk* __restrict__ chunks = a.chunks;
-  double total = 0.0, per_cam = 0.0;
-  int cam = (c0 < c1) ? chunks[c0].cam : 0;
-  for (int cb = c0; cb < c1; cb += 8) {
-    // independent loads of up to 8 chunks first, then the ordered sums
-    double v[8];
-    int cm[8];
+  const int cam0 = (c0 < c1) ? chunks[c0].cam : 0;
+  const bool one_cam = (c0 >= c1) || chunks[c1 - 1].cam == cam0;   // chunks of a block are sorted by camera
+  if (!(one_cam && a.n_shared == SP)) {   // some camera columns of H_os stay empty
+    for (int k = lane; k < 6 * a.n_shared; k += 32) hos[k] = 0.0;
+    __syncwarp();
+  }
+  for (int o = lane; o < 6 * NJ; o += 32) {
+    const int r = o / NJ, j = o - r * NJ;
+    // element of the chunk partial this output sums
+    int src;
+    if (j < 6) src = TE_AA * 64 + r * 8 + j;
+    else if (j == 6) src = TE_AB * 64 + r * 8 + 7;
+    else if (j < 9) src = TE_AA * 64 + r * 8 + (j - 1);       // fx fy: columns 6, 7 of tile A
+    else if (j < 16) src = TE_AB * 64 + r * 8 + (j - 9);      // cx .. k3: columns 0..6 of tile B
+    else src = T_AX * 64 + r * 8 + (j - 16);                  // rig extrinsics
+    const double* __restrict__ part = a.partials + src;
+    double total = 0.0, per_cam = 0.0;
+    int cam = cam0;
+    for (int cb = c0; cb < c1; cb += 8) {
+      // independent loads of up to 8 chunks first, then the ordered sums
+      double v[8];
+      int cm[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = min(cb + u, c1 - 1);
-      v[u] = part[(size_t)c * PART];
-      cm[u] = chunks[c].cam;
-    }
+      for (int u = 0; u < 8; ++u) {
+        const int c = min(cb + u, c1 - 1);
+        v[u] = part[(size_t)c * PART];
+        cm[u] = one_cam ? cam0 : chunks[c].cam;
+      }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (cb + u < c1) {
-        if (cm[u] != cam) {
-          if (j >= 7) hos[r * a.n_shared + cam * SP + (j - 7)] = per_cam;
-          per_cam = 0.0;
-          cam = cm[u];
+      for (int u = 0; u < 8; ++u) {
+        if (cb + u < c1) {
+          if (cm[u] != cam) {
+            if (j >= 7) hos[r * a.n_shared + cam * SP + (j - 7)] = per_cam;
+            per_cam = 0.0;
+            cam = cm[u];
+          }
+          total += v[u];
+          per_cam += v[u];
         }
-        total += v[u];
-        per_cam += v[u];
       }
     }
+    if (j >= 7) {
+      if (c0 < c1) hos[r * a.n_shared + cam * SP + (j - 7)] = per_cam;
+      else if (one_cam && a.n_shared == SP) hos[r * a.n_shared + (j - 7)] = 0.0;   // unobserved block
+    }
+    if (j < 6) a.Hoo[(size_t)i * 36 + r * 6 + j] = total;
+    if (j == 6) a.go[(size_t)i * 6 + r] = total;
   }
-  if (c0 < c1 && j >= 7) hos[r * a.n_shared + cam * SP + (j - 7)] = per_cam;
-  if (j < 6) a.Hoo[(size_t)i * 36 + r * 6 + j] = total;
-  if (j == 6) a.go[(size_t)i * 6 + r] = total;
 }
 
 // ---------------------------------------------------------------------------
 // finalize_shared: shared x shared block, gradient and cost per camera, all from
 // the E-pass partials.  Stage 1: CTA (slice, camera) sums its share of the
-// camera's chunk list for every partial element (fixed order).  Stage 2: one
-// CTA per camera sums the FIN_SLICES partials in order and scatters them into
-// H_ss / g_s / cost.
+// camera's chunk list for every partial element (fixed order).  Stage 2: the
+// last stage-1 CTA of a camera to finish sums the FIN_SLICES partials in slice
+// order and scatters them into H_ss / g_s / cost.
 // ---------------------------------------------------------------------------
+template <bool RIG>
+__device__ __forceinline__ void finalize_shared_final_body(const FinalizeSharedArgs& a, int cam, double* tot);
+
 template <bool RIG>
 __device__ __forceinline__ void finalize_shared_partial_body(const FinalizeSharedArgs& a, int slice, int cam) {
   // warp w of the CTA takes chunks lo + w, lo + w + 8, ... of the slice; lane l keeps elements l, l + 32, ...
@@ -398,6 +411,20 @@ __device__ __forceinline__ void finalize_shared_partial_body(const FinalizeShare
     for (int w = 0; w < 8; ++w) s += red[w][k];
     a.scratch[((size_t)cam * FIN_SLICES + slice) * PART + k] = s;
   }
+  // the last slice of the camera to arrive runs the second stage (fixed summation order: slice 0, 1, ...)
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(a.done_count + cam, 1);
+    is_last = (done == FIN_SLICES - 1);
+    if (is_last) a.done_count[cam] = 0;   // ready for the next launch
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    finalize_shared_final_body<RIG>(a, cam, &red[0][0]);
+  }
 }
 
 // element of the E-pass partial that holds the product of shared parameters i <= j (j == SP: the residual column)
@@ -419,33 +446,19 @@ __device__ __forceinline__ int shared_src(int i, int j) {
   return TE_XX * 64 + (i - 9) * 8 + (j - 9);
 }
 
+// second stage, run by the last first-stage CTA of a camera to finish (see finalize_fused_kernel)
 template <bool RIG>
-__global__ void __launch_bounds__(1024) finalize_shared_final_kernel(const FinalizeSharedArgs a) {
+__device__ __forceinline__ void finalize_shared_final_body(const FinalizeSharedArgs& a, int cam, double* tot) {
   constexpr int SP = PassGeom<RIG>::SP, PART = PassGeom<RIG>::PART_E;
-  constexpr int NQ = 4, SPQ = FIN_SLICES / NQ;       // 4 thread groups sum 16 slices each, then are added in order
-  static_assert(FIN_SLICES % NQ == 0 && PART <= 1024 / NQ * 2, "finalize_shared_final geometry");
-  __shared__ double red[NQ][PART];
-  __shared__ double tot[PART];
-  const int cam = blockIdx.x;
   const int tid = threadIdx.x;
   const int ns = a.n_shared;
   double* H = a.Hss;
   const int base = cam * SP;
   for (int k = tid; k < SP * ns; k += blockDim.x) H[(size_t)base * ns + k] = 0.0;
-  {
-    const int q = tid / 256;
-    for (int k = tid - 256 * q; k < PART; k += 256) {
-      double s = 0.0;
-#pragma unroll
-      for (int sl = 0; sl < SPQ; ++sl) s += a.scratch[((size_t)cam * FIN_SLICES + q * SPQ + sl) * PART + k];
-      red[q][k] = s;
-    }
-  }
-  __syncthreads();
   for (int k = tid; k < PART; k += blockDim.x) {
     double s = 0.0;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) s += red[q][k];
+#pragma unroll 16
+    for (int sl = 0; sl < FIN_SLICES; ++sl) s += __ldcg(a.scratch + ((size_t)cam * FIN_SLICES + sl) * PART + k);
     tot[k] = s;
   }
   __syncthreads();
@@ -463,32 +476,30 @@ __global__ void __launch_bounds__(1024) finalize_shared_final_kernel(const Final
 
 // one launch for the three independent reductions, longest CTAs first: the (slice, camera) first stage of
 // finalize_shared, then the F side (many chunks per kept block), then the E side
+constexpr int FIN_OWN_PER_CTA = 8;   // finalize_side: one warp per own block
 template <bool RIG>
 __global__ void __launch_bounds__(256) finalize_fused_kernel(const FinalizeSideArgs e, const FinalizeSideArgs f,
                                                              const FinalizeSharedArgs sh) {
   int i = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
   if (i < FIN_SLICES * sh.n_cam) {
     finalize_shared_partial_body<RIG>(sh, i % FIN_SLICES, i / FIN_SLICES);
     return;
   }
   i -= FIN_SLICES * sh.n_cam;
-  if (i < f.n_own) {
-    finalize_side_body<RIG, false>(f, i);
+  const int f_ctas = (f.n_own + FIN_OWN_PER_CTA - 1) / FIN_OWN_PER_CTA;
+  if (i < f_ctas) {
+    finalize_side_body<RIG, false>(f, i * FIN_OWN_PER_CTA + warp);
     return;
   }
-  finalize_side_body<RIG, true>(e, i - f.n_own);
+  finalize_side_body<RIG, true>(e, (i - f_ctas) * FIN_OWN_PER_CTA + warp);
 }
 
 void launch_finalize(bool rig, const FinalizeSideArgs& e, const FinalizeSideArgs& f, const FinalizeSharedArgs& sh,
                      cudaStream_t s) {
-  const int grid = e.n_own + f.n_own + FIN_SLICES * sh.n_cam;
-  if (rig) {
-    finalize_fused_kernel<true><<<grid, 256, 0, s>>>(e, f, sh);
-    finalize_shared_final_kernel<true><<<sh.n_cam, 1024, 0, s>>>(sh);
-  } else {
-    finalize_fused_kernel<false><<<grid, 256, 0, s>>>(e, f, sh);
-    finalize_shared_final_kernel<false><<<sh.n_cam, 1024, 0, s>>>(sh);
-  }
+  const int grid = ceil_div(e.n_own, FIN_OWN_PER_CTA) + ceil_div(f.n_own, FIN_OWN_PER_CTA) + FIN_SLICES * sh.n_cam;
+  if (rig) finalize_fused_kernel<true><<<grid, 256, 0, s>>>(e, f, sh);
+  else finalize_fused_kernel<false><<<grid, 256, 0, s>>>(e, f, sh);
   RCC_CUDA(cudaGetLastError());
 }
 

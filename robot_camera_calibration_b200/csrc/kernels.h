@@ -98,10 +98,11 @@ struct FinalizeSharedArgs {
   double* gs;                   // [n_shared]
   double* cost2_cam;            // [n_cam] sum r^2 per camera
   double* scratch;              // [n_cam * FIN_SLICES * PART_E] first-stage partial tiles
+  int32_t* done_count;          // [n_cam] first-stage CTAs finished (zero between launches)
   int32_t robust;               // 1: cost = tail slot (sum rho), else BB[7][7] (sum r^2)
 };
 constexpr int FIN_SLICES = 64;  // CTAs per camera in the first stage of finalize_shared
-// E side, F side and the first stage of the shared reduction in one launch, then the per-camera final stage
+// E side, F side and both stages of the shared reduction in one launch
 void launch_finalize(bool rig, const FinalizeSideArgs& e, const FinalizeSideArgs& f, const FinalizeSharedArgs& sh,
                      cudaStream_t s);
 

@@ -486,11 +486,11 @@ static void do_linearize(P_t* P) {
     launch_assemble(P->rig, false, !P->elim_view, a, P->stream);
   }
   {
-    Scoped t(P, ST_FINALIZE, 2);
+    Scoped t(P, ST_FINALIZE, 1);
     FinalizeSideArgs fe{P->part_e.p, P->e_chunks.p, P->e_chunk_ptr.p, P->n_e, P->n_shared, P->Hee.p, P->ge.p, P->Hes.p};
     FinalizeSideArgs ff{P->part_f.p, P->f_chunks.p, P->f_chunk_ptr.p, P->n_f, P->n_shared, P->Hff.p, P->gf.p, P->Hfs.p};
-    FinalizeSharedArgs fs{P->part_e.p, P->cam_chunks_e.p, P->cam_ptr_e.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p, P->cost2_cam.p, P->fin_scratch.p,
-                          P->loss != 0 ? 1 : 0};
+    FinalizeSharedArgs fs{P->part_e.p, P->cam_chunks_e.p, P->cam_ptr_e.p, P->n_cam, P->n_shared, P->Hss.p, P->gs.p,
+                          P->cost2_cam.p, P->fin_scratch.p, P->fin_done.p, P->loss != 0 ? 1 : 0};
     launch_finalize(P->rig, fe, ff, fs, P->stream);
   }
   P->linearized = true;
@@ -888,6 +888,7 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     P->Hee.alloc((size_t)P->n_e * 36); P->ge.alloc((size_t)P->n_e * 6); P->Hes.alloc((size_t)P->n_e * 6 * P->n_shared);
     P->Hff.alloc((size_t)P->n_f * 36); P->gf.alloc((size_t)P->n_f * 6); P->Hfs.alloc((size_t)P->n_f * 6 * P->n_shared);
     P->fin_scratch.alloc((size_t)P->n_cam * FIN_SLICES * PassGeom<true>::PART_E);
+    P->fin_done.alloc((size_t)P->n_cam); P->fin_done.zero(s);
     P->Hss.alloc((size_t)P->n_shared * P->n_shared); P->gs.alloc((size_t)P->n_shared); P->cost2_cam.alloc(P->n_cam);
     P->Linv.alloc((size_t)P->n_e * 36); P->Yb.alloc((size_t)P->n_e * P->n_bb * 36); P->d2e.alloc((size_t)P->n_e * 6);
     P->S.alloc((size_t)(P->n_red + 3) * P->ld); P->S.zero(s);

@@ -82,7 +82,7 @@ struct rcc_ba_problem {
   rcc::DBuf<double> fin_scratch, part_e, part_f, W, Hee, ge, Hes, Hff, gf, Hfs, Hss, gs, cost2_cam;
   // Schur / step
   rcc::DBuf<double> Linv, Y, Yb, d2e, S, shared_scratch, rhs, d2f, gFm, delta_F, delta_e, bs_partials, stats;
-  rcc::DBuf<int32_t> const_idx, fail_flag;
+  rcc::DBuf<int32_t> const_idx, fail_flag, fin_done;
   int n_const = 0;
   double radius_used = 0.0;
   // evaluation outputs
