@@ -161,7 +161,11 @@ void launch_schur_prep(const SchurPrepArgs& a, cudaStream_t s) {
 constexpr int SY_WARPS = RCC_SY_WARPS;
 constexpr int SY_SUB = RCC_SY_SUB;   // kept blocks per warp sub-tile: a multiple of SchurSyrkArgs::tile_w (32)
 constexpr int SY_G = SY_SUB / 32;    // tile_ptr entries per warp sub-tile
-constexpr int SY_BATCH = 32;         // pairs of column f staged per round
+#ifndef RCC_SY_BATCH
+#define RCC_SY_BATCH 32
+#endif
+constexpr int SY_BATCH = RCC_SY_BATCH;   // pairs of column f staged per round (<= 32: one lane per pair holds its range)
+static_assert(SY_BATCH <= 32, "a batch must fit the lanes of a warp");
 static_assert(SY_SUB % 32 == 0, "warp sub-tile must be a multiple of the tile_ptr granularity");
 int schur_cta_subtiles() { return SY_WARPS * SY_G; }
 
