@@ -61,6 +61,21 @@ def workload(cfg, rank, scale):
     return s, desc
 
 
+def bind_near_gpu(torch, local):
+    """Best effort: run this rank on the CPUs NVML calls ideal for its GPU, so that first-touch puts the
+    pinned host buffers of the end-to-end path on the GPU's NUMA node (a remote node halves H2D bandwidth)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus_before": before, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as e:  # not permitted in this cgroup, NVML missing, ...
+        return {"unchanged": str(e)[:100]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -191,6 +206,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    cpus_all = os.sched_getaffinity(0)
+    placement = bind_near_gpu(torch, local)      # pinned host buffers must sit on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -298,6 +315,17 @@ def run_ours(args):
     for _ in range(2):
         e2e_step()
     barrier()
+    d_probe = torch.empty(h_pix.size, dtype=torch.float64, device="cuda")
+    t_probe = torch.from_numpy(h_pix)
+    h2d_ms = []
+    for _ in range(3):
+        a, b = ev(), ev()
+        a.record(); d_probe.view(t_probe.shape).copy_(t_probe, non_blocking=True); b.record()
+        torch.cuda.synchronize()
+        h2d_ms.append(a.elapsed_time(b))
+    h2d_gbs = h_pix.nbytes / (min(h2d_ms) * 1e-3) / 1e9
+    del d_probe
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
@@ -335,6 +363,7 @@ def run_ours(args):
         ach = BYTES_PER_BLOCK_E * n_blocks / (k_ms * 1e-3) / 1e9
         value = obs_all * args.steps / (total_ms_max * 1e-3)
         step_flops = FLOP_PER_BLOCK * n_blocks
+        os.sched_setaffinity(0, cpus_all)        # the CPU baseline may use every host core again
         base = cpu_baseline(scene, seconds=args.cpu_seconds)[0] if world == 1 else None
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -375,6 +404,7 @@ def run_ours(args):
             "cpu_baseline": base,
             "e2e": {"value": obs_all * args.steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                    "h2d_gb_per_s_this_box": h2d_gbs, "cpu_placement": placement,
                     "what": "set_view/marker_poses + set_intrinsics + update_pixels (pinned host -> device), "
                             "linearize, read back cost and gradient"},
             "gpu_launches": launches_all,
