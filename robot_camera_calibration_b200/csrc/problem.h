@@ -49,7 +49,7 @@ struct rcc_ba_problem {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   // fork/join side stream: small kernels that only depend on the previous stage run beside the big one
-  cudaStream_t side_stream = nullptr;
+  cudaStream_t side_stream = nullptr, side_stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // piecewise pixel upload (rcc_ba_update_pixels when the caller order is the E-sorted order): the H2D
   // copy runs on the side stream in PIX_PIECES pieces cut at chunk boundaries, and the next linearize
