@@ -220,3 +220,37 @@ def test_huber_resists_outliers():
             gp.solve(max_iterations=60)
             err[loss] = np.abs(gp.get_marker_poses()[:, 3:] - s.truth["markers"][:, 3:]).max()
     assert err["huber"] < 0.5 * err["trivial"]
+
+
+def test_converged_parameters_match_an_independent_solver():
+    """The GPU LM (Schur + trust region written here) and SciPy's trust-region-reflective least-squares
+    solver (driven by the oracle's residuals and complex-step Jacobian) must find the same minimiser:
+    1e-6 rad / 1e-6 m on poses (BASELINE.json north_star).  Pins the LM driver to a solver that shares
+    no code with it."""
+    from scipy.optimize import least_squares
+    s = make_scene(8, 14, 0.9, seed=61)
+    p = to_oracle(s)
+    free = ~p.const_mask()
+    x0 = p.pack()
+
+    def with_x(xf):
+        q = p.copy()
+        x = x0.copy()
+        x[free] = xf
+        q.unpack(x)
+        return q
+
+    sol = least_squares(lambda xf: O.residuals(with_x(xf)).ravel(), x0[free],
+                        jac=lambda xf: O.dense_jacobian(with_x(xf))[:, free], method="trf", x_scale="jac",
+                        ftol=1e-15, xtol=1e-15, gtol=1e-13, max_nfev=200)
+    ref = with_x(sol.x)
+    with BAProblem.from_scene(s) as gp:
+        summ = gp.solve(max_iterations=100, function_tolerance=1e-16, gradient_tolerance=1e-13,
+                        parameter_tolerance=1e-15)
+        views, markers = gp.get_view_poses(), gp.get_marker_poses()
+        intr, dist = gp.get_intrinsics()
+    assert abs(summ["final_cost"] - O.cost(ref)) <= 1e-9 * O.cost(ref)
+    assert np.abs(views - ref.views).max() < 1e-6
+    assert np.abs(markers - ref.markers).max() < 1e-6
+    assert np.abs(dist - ref.dist).max() < 1e-6
+    assert np.abs(intr - ref.intr).max() < 1e-4      # pixels
