@@ -20,6 +20,7 @@ namespace rcc {
 // ---------------------------------------------------------------------------
 // schur_prep: one warp per eliminated block
 // ---------------------------------------------------------------------------
+constexpr int PREP_REC = 38;   // staged 6x6 record stride (doubles): 36 + 2 keeps the 16-byte row reads of 8 lanes on distinct banks
 __global__ void __launch_bounds__(128) schur_prep_kernel(const SchurPrepArgs a) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,30 +86,74 @@ __global__ void __launch_bounds__(128) schur_prep_kernel(const SchurPrepArgs a) 
       for (int j = 0; j < 6; ++j) a.Linv[(size_t)e * 36 + i * 6 + j] = Li[i][j];
     }
   }
-  // Y = L^-1 * (sum of the member W blocks) for every pair of row e
-  for (int p = a.row_ptr[e] + lane; p < a.row_ptr[e + 1]; p += 32) {
+  // Y = L^-1 * (sum of the member W blocks) for every pair of row e, 32 pairs per round.  The 288-byte
+  // W and Y records of a round are contiguous in HBM when every pair has one member at consecutive sorted
+  // positions (always in the single-camera model): they then cross the SM through shared memory so that
+  // the global accesses are coalesced 16-byte pieces instead of 32 strided records per instruction.
+  __shared__ __align__(16) double rec_all[4][32 * PREP_REC];
+  double* rec = rec_all[threadIdx.x >> 5];
+  const int p_end = a.row_ptr[e + 1];
+  for (int p0 = a.row_ptr[e]; p0 < p_end; p0 += 32) {
+    const int np = min(32, p_end - p0);
+    const int p = p0 + lane;
+    const bool on = lane < np;
+    int m0 = 0, m1 = 0, pos = 0;
+    if (on) {
+      m0 = a.pair_mptr[p];
+      m1 = a.pair_mptr[p + 1];
+      pos = a.pair_members[m0];
+    }
+    const int pos0 = __shfl_sync(0xffffffffu, pos, 0);
+    const bool fast = __all_sync(0xffffffffu, !on || (m1 - m0 == 1 && pos == pos0 + lane));
     double Wm[36];
-#pragma unroll
-    for (int i = 0; i < 36; ++i) Wm[i] = 0.0;
-    for (int m = a.pair_mptr[p]; m < a.pair_mptr[p + 1]; ++m) {
-      const double2* w = reinterpret_cast<const double2*>(a.W + (size_t)a.pair_members[m] * 36);
+    if (fast) {
+      const double2* src = reinterpret_cast<const double2*>(a.W + (size_t)pos0 * 36);
+      for (int k = lane; k < np * 18; k += 32) {
+        const int q = k / 18;
+        reinterpret_cast<double2*>(rec + q * PREP_REC)[k - q * 18] = src[k];
+      }
+      __syncwarp();
 #pragma unroll
       for (int i = 0; i < 18; ++i) {
-        const double2 v = w[i];
-        Wm[2 * i] += v.x;
-        Wm[2 * i + 1] += v.y;
+        const double2 v = reinterpret_cast<const double2*>(rec + lane * PREP_REC)[i];
+        Wm[2 * i] = v.x;
+        Wm[2 * i + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) Wm[i] = 0.0;
+      for (int m = m0; m < m1; ++m) {
+        const double2* w = reinterpret_cast<const double2*>(a.W + (size_t)a.pair_members[m] * 36);
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+          const double2 v = w[i];
+          Wm[2 * i] += v.x;
+          Wm[2 * i + 1] += v.y;
+        }
       }
     }
-    double* y = a.Y + (size_t)p * 36;
+    // y = L^-1 Wm, column-major; staged through the same record when the round is contiguous
+    double* y = fast ? rec + lane * PREP_REC : a.Y + (size_t)p * 36;
+    if (on) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c)
+      for (int c = 0; c < 6; ++c)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        double v = 0.0;
+        for (int k = 0; k < 6; ++k) {
+          double v = 0.0;
 #pragma unroll
-        for (int j = 0; j <= k; ++j) v += Li[k][j] * Wm[j * 6 + c];
-        y[c * 6 + k] = v;  // column-major
+          for (int j = 0; j <= k; ++j) v += Li[k][j] * Wm[j * 6 + c];
+          y[c * 6 + k] = v;  // column-major
+        }
+    }
+    if (fast) {
+      __syncwarp();
+      double2* dst = reinterpret_cast<double2*>(a.Y + (size_t)p0 * 36);
+      for (int k = lane; k < np * 18; k += 32) {
+        const int q = k / 18;
+        dst[k] = reinterpret_cast<const double2*>(rec + q * PREP_REC)[k - q * 18];
       }
+      __syncwarp();
+    }
   }
   // border: columns 0..n_shared-1 = H_es, column n_shared = g_e, rest zero
   const int ncol = a.n_bb * 6;
@@ -572,15 +617,30 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   const int lane = threadIdx.x & 31;
   if (e >= a.n_e) return;
   double v[6] = {0, 0, 0, 0, 0, 0};
-  for (int p = a.row_ptr[e] + lane; p < a.row_ptr[e + 1]; p += 32) {
-    const double* y = a.Y + (size_t)p * 36;
-    const double* d = a.delta_F + (size_t)a.pair_f[p] * 6;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      const double dc = d[c];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v[k] = fma(y[c * 6 + k], dc, v[k]);
+  // 32 pairs per round: their Y records (contiguous in HBM) cross the SM through shared memory as
+  // coalesced 16-byte pieces; each lane then multiplies its own record with its kept block's step
+  __shared__ __align__(16) double rec_all[4][32 * PREP_REC];
+  double* rec = rec_all[threadIdx.x >> 5];
+  const int p_end = a.row_ptr[e + 1];
+  for (int p0 = a.row_ptr[e]; p0 < p_end; p0 += 32) {
+    const int np = min(32, p_end - p0);
+    const double2* src = reinterpret_cast<const double2*>(a.Y + (size_t)p0 * 36);
+    for (int k = lane; k < np * 18; k += 32) {
+      const int q = k / 18;
+      reinterpret_cast<double2*>(rec + q * PREP_REC)[k - q * 18] = src[k];
     }
+    __syncwarp();
+    if (lane < np) {
+      const double* y = rec + lane * PREP_REC;
+      const double* d = a.delta_F + (size_t)a.pair_f[p0 + lane] * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double dc = d[c];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = fma(y[c * 6 + k], dc, v[k]);
+      }
+    }
+    __syncwarp();
   }
   // border: shared columns times d_shared, plus the g_e column (coefficient 1)
   const double* ds = a.delta_F + (size_t)6 * a.n_f;
