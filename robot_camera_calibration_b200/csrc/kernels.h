@@ -165,6 +165,8 @@ struct SchurPrepArgs {
   const int32_t* row_ptr;        // [n_e+1] pairs of row e
   const int32_t* pair_mptr;      // [n_pairs+1]
   const int32_t* pair_members;   // sorted-observation positions
+  const int32_t* row_pos0;       // [n_e] first sorted position of row e when its pairs have one member each at
+                                 // consecutive positions (then W of pair p0+i is W[row_pos0 + i]); -1 otherwise
   const double* W;               // [n_obs*36]
   double radius, min_diag, max_diag;
   double* Linv;                  // [n_e*36] row-major lower-triangular inverse of chol(Hee + D)

@@ -330,6 +330,22 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
     pair_mptr.push_back((int32_t)members.size());
   }
   P->n_pairs = (int64_t)pair_e.size();
+  {
+    // rows whose pairs have exactly one member each, at consecutive sorted positions (every row of a
+    // single-camera problem): schur_prep then needs no per-pair index loads
+    std::vector<int32_t> row_pos0((size_t)std::max(P->n_e, 1), -1);
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < P->n_e; ++e) {
+      const int p0 = row_ptr[e], p1 = row_ptr[e + 1];
+      if (p1 <= p0) continue;
+      const int first = members[pair_mptr[p0]];
+      bool ok = true;
+      for (int p = p0; p < p1 && ok; ++p)
+        ok = (pair_mptr[p + 1] - pair_mptr[p] == 1) && (members[pair_mptr[p]] == first + (p - p0));
+      if (ok) row_pos0[e] = first;
+    }
+    P->row_pos0.upload(row_pos0, s);
+  }
   P->row_ptr.upload(row_ptr, s);
   P->pair_e.upload(pair_e, s);
   P->pair_f.upload(pair_f, s);
@@ -509,7 +525,7 @@ static void do_schur(P_t* P, double radius) {
     SchurPrepArgs a{};
     a.n_e = P->n_e; a.n_shared = P->n_shared; a.n_bb = P->n_bb;
     a.Hee = P->Hee.p; a.ge = P->ge.p; a.Hes = P->Hes.p; a.e_const = P->e_const.p;
-    a.row_ptr = P->row_ptr.p; a.pair_mptr = P->pair_mptr.p; a.pair_members = P->pair_members.p; a.W = P->W.p;
+    a.row_ptr = P->row_ptr.p; a.pair_mptr = P->pair_mptr.p; a.pair_members = P->pair_members.p; a.row_pos0 = P->row_pos0.p; a.W = P->W.p;
     a.radius = radius; a.min_diag = P->min_diag; a.max_diag = P->max_diag;
     a.Linv = P->Linv.p; a.Y = P->Y.p; a.Yb = P->Yb.p; a.d2e = P->d2e.p;
     launch_schur_prep(a, P->stream);

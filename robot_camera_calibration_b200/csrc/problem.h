@@ -75,7 +75,7 @@ struct rcc_ba_problem {
   rcc::DBuf<double> e_pix, f_pix, pix_staging;
   rcc::DBuf<rcc::Chunk> e_chunks, f_chunks;
   rcc::DBuf<int32_t> cam_chunks_e, cam_ptr_e, cam_chunks_f, cam_ptr_f;
-  rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, col_ptr, col_pair, tile_ptr, syrk_ctas, e_count;
+  rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, row_pos0, col_ptr, col_pair, tile_ptr, syrk_ctas, e_count;
   rcc::DBuf<uint8_t> e_const;
 
   // linearisation products

@@ -92,19 +92,19 @@ __global__ void __launch_bounds__(128) schur_prep_kernel(const SchurPrepArgs a) 
   // the global accesses are coalesced 16-byte pieces instead of 32 strided records per instruction.
   __shared__ __align__(16) double rec_all[4][32 * PREP_REC];
   double* rec = rec_all[threadIdx.x >> 5];
-  const int p_end = a.row_ptr[e + 1];
-  for (int p0 = a.row_ptr[e]; p0 < p_end; p0 += 32) {
+  const int p_begin = a.row_ptr[e], p_end = a.row_ptr[e + 1];
+  const int row_pos0 = a.row_pos0[e];
+  const bool fast = row_pos0 >= 0;   // warp-uniform; no per-pair index loads on this path
+  for (int p0 = p_begin; p0 < p_end; p0 += 32) {
     const int np = min(32, p_end - p0);
     const int p = p0 + lane;
     const bool on = lane < np;
-    int m0 = 0, m1 = 0, pos = 0;
-    if (on) {
+    int m0 = 0, m1 = 0;
+    if (on && !fast) {
       m0 = a.pair_mptr[p];
       m1 = a.pair_mptr[p + 1];
-      pos = a.pair_members[m0];
     }
-    const int pos0 = __shfl_sync(0xffffffffu, pos, 0);
-    const bool fast = __all_sync(0xffffffffu, !on || (m1 - m0 == 1 && pos == pos0 + lane));
+    const int pos0 = row_pos0 + (p0 - p_begin);
     double Wm[36];
     if (fast) {
       const double2* src = reinterpret_cast<const double2*>(a.W + (size_t)pos0 * 36);
