@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
         list(ex.map(compile_one, jobs))
     if jobs or force or _stale(LIB, objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + [
-            "-Xcompiler", "-fopenmp", "-lcusolver", "-lnccl", "-lgomp",
+            "-Xcompiler", "-fopenmp", "-lcusolver", "-lcublas", "-lnccl", "-lgomp",
             "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

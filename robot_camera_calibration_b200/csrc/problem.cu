@@ -87,6 +87,7 @@ struct Scoped {
 rcc_ba_problem::~rcc_ba_problem() {
   if (comm) ncclCommDestroy(comm);
   if (solver) cusolverDnDestroy(solver);
+  if (blas) cublasDestroy(blas);
   if (h_pinned) cudaFreeHost(h_pinned);
   for (auto& hs : hslot) {
     if (hs.p) cudaFreeHost(hs.p);
@@ -107,6 +108,12 @@ typedef rcc_ba_problem P_t;
   do {                                                                                                         \
     ncclResult_t _r = (expr);                                                                                  \
     if (_r != ncclSuccess) throw Error(RCC_NCCL_ERROR, std::string(#expr) + ": " + ncclGetErrorString(_r));   \
+  } while (0)
+#define RCC_BLAS(expr)                                                                             \
+  do {                                                                                             \
+    cublasStatus_t _r = (expr);                                                                    \
+    if (_r != CUBLAS_STATUS_SUCCESS)                                                               \
+      throw Error(RCC_SOLVER_ERROR, std::string(#expr) + ": cublas status " + std::to_string((int)_r)); \
   } while (0)
 #define RCC_SOLVER(expr)                                                                              \
   do {                                                                                                \
@@ -589,6 +596,13 @@ __global__ void gmaxf_kernel(const double* __restrict__ g, int n, double* __rest
   if (threadIdx.x == 0) out[0] = red[0];
 }
 __global__ void copy_scalar_kernel(const double* src, double* dst) { dst[0] = src[0]; }
+// pivot of the border row of the bordered Cholesky: anything larger than b^T S^-1 b keeps it positive
+__global__ void set_border_pivot_kernel(double* p) { p[0] = 1e300; }
+// rhs = -(L^-1 b): the border row of the factor (column n of the row-major buffer), negated for S x = -b
+__global__ void extract_rhs_kernel(const double* __restrict__ S, int n, int ld, double* __restrict__ rhs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rhs[i] = -S[(size_t)i * ld + n];
+}
 
 // all-reduce + damping/mask + Cholesky + back-substitution + candidate parameters
 static void do_step(P_t* P) {
@@ -607,10 +621,18 @@ static void do_step(P_t* P) {
     copy_scalar_kernel<<<1, 1, 0, P->stream>>>(P->S.p + (size_t)n * P->ld + 2 * n, P->stats.p + SX_COST2);
   }
   {
-    Scoped t(P, ST_CHOLESKY, 2);
-    RCC_SOLVER(cusolverDnDpotrf(P->solver, CUBLAS_FILL_MODE_LOWER, n, P->S.p, P->ld, P->potrf_work.p, P->potrf_lwork,
-                                P->dev_info.p));
-    RCC_SOLVER(cusolverDnDpotrs(P->solver, CUBLAS_FILL_MODE_LOWER, n, 1, P->S.p, P->ld, P->rhs.p, n, P->dev_info.p + 1));
+    // Bordered factorisation: the rhs already sits in column n of the row-major upper triangle, i.e. in row n
+    // of the column-major lower triangle cuSOLVER sees.  Factoring the (n+1) x (n+1) matrix [[S, b], [b^T, big]]
+    // leaves y = L^-1 b in that row -- the forward substitution comes out of potrf for free -- and one
+    // triangular solve L^T x = -y remains (cusolverDnDpotrs would run two).
+    Scoped t(P, ST_CHOLESKY, 4);
+    set_border_pivot_kernel<<<1, 1, 0, P->stream>>>(P->S.p + (size_t)n * P->ld + n);
+    RCC_SOLVER(cusolverDnDpotrf(P->solver, CUBLAS_FILL_MODE_LOWER, n + 1, P->S.p, P->ld, P->potrf_work.p,
+                                P->potrf_lwork, P->dev_info.p));
+    extract_rhs_kernel<<<ceil_div(n, 256), 256, 0, P->stream>>>(P->S.p, n, P->ld, P->rhs.p);
+    RCC_CUDA(cudaGetLastError());
+    RCC_BLAS(cublasDtrsv(P->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n, P->S.p, P->ld,
+                         P->rhs.p, 1));
   }
   {
     Scoped t(P, ST_BACKSUB, 8);
@@ -921,7 +943,10 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     P->scalar.alloc(8);
     RCC_SOLVER(cusolverDnCreate(&P->solver));
     RCC_SOLVER(cusolverDnSetStream(P->solver, s));
-    RCC_SOLVER(cusolverDnDpotrf_bufferSize(P->solver, CUBLAS_FILL_MODE_LOWER, P->n_red, P->S.p, P->ld, &P->potrf_lwork));
+    RCC_SOLVER(cusolverDnDpotrf_bufferSize(P->solver, CUBLAS_FILL_MODE_LOWER, P->n_red + 1, P->S.p, P->ld,
+                                           &P->potrf_lwork));   // + the border row (see do_step)
+    RCC_BLAS(cublasCreate(&P->blas));
+    RCC_BLAS(cublasSetStream(P->blas, s));
     P->potrf_work.alloc((size_t)std::max(1, P->potrf_lwork));
     RCC_CUDA(cudaStreamSynchronize(s));
   } catch (const Error& e) {
@@ -953,6 +978,7 @@ int rcc_ba_set_stream(rcc_ba_problem* P, void* cuda_stream) {
   P->stream = (cudaStream_t)cuda_stream;
   P->own_stream = false;
   RCC_SOLVER(cusolverDnSetStream(P->solver, P->stream));
+  RCC_BLAS(cublasSetStream(P->blas, P->stream));
   API_END(P)
 }
 

@@ -1,6 +1,7 @@
 // Host-side problem object behind the opaque C handle.
 #pragma once
 
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <nccl.h>
 
@@ -89,6 +90,7 @@ struct rcc_ba_problem {
   rcc::DBuf<double> o_res, o_ji, o_jd, o_jv, o_jm, o_jx, cost_partials, scalar;
 
   cusolverDnHandle_t solver = nullptr;
+  cublasHandle_t blas = nullptr;
   rcc::DBuf<double> potrf_work;
   rcc::DBuf<int> dev_info;
   int potrf_lwork = 0;

@@ -21,7 +21,7 @@ namespace rcc {
 // schur_prep: one warp per eliminated block
 // ---------------------------------------------------------------------------
 constexpr int PREP_REC = 38;   // staged 6x6 record stride (doubles): 36 + 2 keeps the 16-byte row reads of 8 lanes on distinct banks
-__global__ void __launch_bounds__(128) schur_prep_kernel(const SchurPrepArgs a) {
+__global__ void __launch_bounds__(128, 3) schur_prep_kernel(const SchurPrepArgs a) {
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (e >= a.n_e) return;
@@ -594,6 +594,7 @@ __global__ void mask_kernel(const MaskArgs a) {
   }
   if (threadIdx.x == 0) {
     a.S[(size_t)c * a.ld + c] = 1.0;
+    a.S[(size_t)c * a.ld + a.n] = 0.0;   // rhs column of the bordered factorisation
     a.rhs[c] = 0.0;
     a.d2f[c] = 0.0;
     a.gF[c] = 0.0;

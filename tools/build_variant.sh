@@ -11,5 +11,5 @@ for f in assemble evaluate schur problem pnp; do
 done
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/librcc_ba_$name.so $out/$name/*.o \
-  -Xcompiler -fopenmp -lcusolver -lnccl -lgomp -Xlinker -rpath,/usr/local/cuda/lib64
+  -Xcompiler -fopenmp -lcusolver -lcublas -lnccl -lgomp -Xlinker -rpath,/usr/local/cuda/lib64
 echo $out/librcc_ba_$name.so
