@@ -62,7 +62,6 @@ struct AssembleArgs {
   const double* marker_x; // [n_markers*24]
   const double* ext_x;    // [n_cam*24] (rig)
   const double* shared;   // [n_cam*SP]
-  const double* sizes;    // [n_markers]
   // outputs
   double* partials;       // [n_chunks * PART_E|PART_F]: 8x8 tiles, element (m, n) at m * 8 + n
   double* W;              // [n*36] (E pass only) row-major 6x6: rows own, cols other
@@ -125,7 +124,6 @@ struct EvalArgs {
   const double* marker_x;
   const double* ext_x;
   const double* shared;
-  const double* sizes;
   // outputs (caller order; any may be null)
   double* residuals;        // [n*8]
   double* jac_intr;         // [n*8*4]

@@ -468,7 +468,6 @@ static void do_linearize(P_t* P) {
   a.marker_x = P->marker_x.p;
   a.ext_x = P->ext_x.p;
   a.shared = P->shared.p;
-  a.sizes = P->sizes.p;
   a.fail_flag = P->fail_flag.p;
   a.loss = P->loss;
   a.loss_a2 = P->loss_scale * P->loss_scale;
@@ -670,7 +669,6 @@ static EvalArgs eval_args(P_t* P, bool cand) {
   a.marker_x = cand ? P->marker_xc.p : P->marker_x.p;
   a.ext_x = cand ? P->ext_xc.p : P->ext_x.p;
   a.shared = cand ? P->shared_c.p : P->shared.p;
-  a.sizes = P->sizes.p;
   a.cost2_partials = P->cost_partials.p;
   a.chunks = P->e_chunks.p;
   a.n_chunks = P->n_chunks_e;

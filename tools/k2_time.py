@@ -1,5 +1,5 @@
 """Times the linearisation stages on one workload (kernel-tuning helper).
-env: RCC_BA_LIB (variant library), RCC_CHUNK, RCC_TILE_W.  usage: k2_time.py [cfg] [scale] [steps]"""
+env: RCC_BA_LIB (variant library), RCC_CHUNK.  usage: k2_time.py [cfg] [scale] [steps]"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -22,7 +22,7 @@ gp.synchronize()
 pr = gp.profile()
 out = {k: round(v[0] / steps * 1e3, 1) for k, v in pr.items() if v[0] > 0}
 tot = sum(out.values())
-res = {"lib": os.path.basename(os.environ.get("RCC_BA_LIB", "default")), "chunk": os.environ.get("RCC_CHUNK", "48"),
+res = {"lib": os.path.basename(os.environ.get("RCC_BA_LIB", "default")), "chunk": os.environ.get("RCC_CHUNK", "64"),
        "blocks": scene.n_blocks, "us": out, "obs_per_s": 4 * scene.n_blocks / (tot * 1e-6)}
 if lm:
     gp.profile_reset()
@@ -30,5 +30,5 @@ if lm:
         gp.linearize(want_cost=False); gp.schur(1e4); gp.solve_step(); gp.candidate_cost()
     gp.synchronize()
     res["lm_us"] = {k: round(v[0] / lm * 1e3, 1) for k, v in gp.profile().items() if v[0] > 0}
-    res["tile_w"] = os.environ.get("RCC_TILE_W", "128")
+    pass
 print(json.dumps(res))
