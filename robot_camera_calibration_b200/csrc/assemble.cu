@@ -513,7 +513,7 @@ __global__ void expand_poses_kernel(const double* __restrict__ views, int n_view
     expand_pose(views + (size_t)i * 6, view_x + (size_t)i * POSEX);
   } else if (i < n_views + n_markers) {
     const int j = i - n_views;
-    expand_pose(markers + (size_t)j * 6, marker_x + (size_t)j * POSEX);
+    expand_marker_pose(markers + (size_t)j * 6, marker_x + (size_t)j * POSEX);
     marker_x[(size_t)j * POSEX + PX_HS] = 0.5 * sizes[j];  // half tag size rides in the record's padding
   } else if (i < n_views + n_markers + n_cam && sp == 15) {
     const int j = i - n_views - n_markers;

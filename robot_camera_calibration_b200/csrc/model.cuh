@@ -24,8 +24,11 @@ namespace rcc {
 
 // expanded pose: R (row-major 3x3), Jr = right Jacobian of SO(3) at rvec, t.
 // stored as 24 doubles (21 used) so one pose is 6 x 32-byte sectors.
+// MARKER records hold R * Jr in the Jr slot (expand_marker_pose): the only use of a marker's Jr is
+// K_m = cam_R_marker * Jr = M_t * (R_m Jr), which then no longer waits for cam_R_marker.
 constexpr int POSEX = 24;
 constexpr int PX_R = 0, PX_JR = 9, PX_T = 18;
+constexpr int PX_RJ = PX_JR;   // marker records
 constexpr int PX_HS = 21;  // marker records: half tag size (filled by expand_poses_kernel)
 
 // sin(t)/t, accurate for all t >= 0
@@ -76,6 +79,18 @@ RCC_HD void expand_pose(const double* __restrict__ p, double* __restrict__ o) {
   o[PX_T + 1] = p[4];
   o[PX_T + 2] = p[5];
   o[21] = 0.0; o[22] = 0.0; o[23] = 0.0;
+}
+
+// C = A B
+RCC_HD void mat3_AB(const double* A, const double* B, double* C);
+
+// marker pose: R, R * Jr, t
+RCC_HD void expand_marker_pose(const double* __restrict__ p, double* __restrict__ o) {
+  expand_pose(p, o);
+  double rj[9];
+  mat3_AB(o + PX_R, o + PX_JR, rj);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[PX_RJ + i] = rj[i];
 }
 
 // C = A^T B   (3x3 row-major)
@@ -148,9 +163,10 @@ RCC_HD void block_geometry(const double* __restrict__ vx, const double* __restri
 #pragma unroll
   for (int i = 0; i < 9; ++i) g.Jrv[i] = vx[PX_JR + i];
   if (!RIG) {
+    // [Rcm | Km | c0] = Rv^T [Rm | Rm Jr(rm) | tm - tv]: three independent products
     mat3_AtB(vx + PX_R, mx + PX_R, g.Rcm);
     mat3_Atx(vx + PX_R, dt, g.c0);
-    mat3_AB(g.Rcm, mx + PX_JR, g.Km);
+    mat3_AtB(vx + PX_R, mx + PX_RJ, g.Km);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -161,7 +177,6 @@ RCC_HD void block_geometry(const double* __restrict__ vx, const double* __restri
     mat3_AtB(xx + PX_R, g.Rbm, g.Rcm);
     double q[3] = {g.qb0[0] - xx[PX_T + 0], g.qb0[1] - xx[PX_T + 1], g.qb0[2] - xx[PX_T + 2]};
     mat3_Atx(xx + PX_R, q, g.c0);
-    mat3_AB(g.Rcm, mx + PX_JR, g.Km);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -173,6 +188,7 @@ RCC_HD void block_geometry(const double* __restrict__ vx, const double* __restri
       for (int j = 0; j < 3; ++j)
         g.Mt[3 * i + j] = xx[PX_R + 0 + i] * vx[PX_R + 3 * j + 0] + xx[PX_R + 3 + i] * vx[PX_R + 3 * j + 1] +
                           xx[PX_R + 6 + i] * vx[PX_R + 3 * j + 2];
+    mat3_AB(g.Mt, mx + PX_RJ, g.Km);   // Rcm Jr(rm) = (Rx^T Rb^T)(Rm Jr(rm))
 #pragma unroll
     for (int i = 0; i < 9; ++i) g.Jrx[i] = xx[PX_JR + i];
   }

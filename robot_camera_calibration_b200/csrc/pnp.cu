@@ -73,7 +73,7 @@ __device__ double pnp_cost(const double* p, const double* sh, double hs, const d
   double idx[POSEX], px[POSEX];
   const double zero[6] = {0, 0, 0, 0, 0, 0};
   expand_pose(zero, idx);
-  expand_pose(p, px);
+  expand_marker_pose(p, px);   // the tag pose plays the marker role: its Jr slot holds R Jr
   BlockGeom<false> geo;
   block_geometry<false>(idx, px, nullptr, geo);
   double cost = 0.0;

@@ -10,7 +10,7 @@ static void run(const double* view6, const double* marker6, const double* ext6, 
                 const double* pix8, double* r8, double* jv, double* jm, double* js, double* jx, double* depth4) {
   double vx[POSEX], mx[POSEX], xx[POSEX];
   expand_pose(view6, vx);
-  expand_pose(marker6, mx);
+  expand_marker_pose(marker6, mx);
   if (RIG) expand_pose(ext6, xx);
   BlockGeom<RIG> g;
   block_geometry<RIG>(vx, mx, RIG ? xx : nullptr, g);
