@@ -61,3 +61,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "ba_oracle" not in txt and "cpu_baseline" not in txt and "cpu_restatement" not in txt, f
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/rcc_ba.h is the drop-in boundary: it must compile as C99 (no C++, no torch types) and a C
+    translation unit written like INTEGRATION.md's stub must link against librcc_ba.so."""
+    import subprocess
+    from robot_camera_calibration_b200 import _lib as L
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include "rcc_ba.h"\n'
+        "int main(void) {\n"
+        "  rcc_ba_options opt = {RCC_MODEL_SINGLE, 2, 2, 1, 0, 0, RCC_ELIM_AUTO};\n"
+        "  rcc_ba_problem* p = 0;\n"
+        "  rcc_lm_options lm; rcc_lm_default_options(&lm);\n"
+        "  /* no device on the build box: creation must fail cleanly, never fall back */\n"
+        "  int rc = rcc_ba_create(&opt, &p);\n"
+        "  return (rc == RCC_OK) ? (rcc_ba_destroy(p), 0) : (rcc_ba_last_error(0) ? 0 : 1);\n"
+        "}\n")
+    exe = tmp_path / "caller"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe),
+                    L.LIB_PATH, "-Wl,-rpath," + os.path.dirname(L.LIB_PATH), "-Wl,-rpath,/usr/local/cuda/lib64"],
+                   check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
