@@ -180,6 +180,10 @@ int rcc_ba_get_normal_blocks(rcc_ba_problem* p, double* Hee, double* ge, double*
 /* reduced system after rcc_ba_schur (+ all-reduce/mask if rcc_ba_solve_step ran):
  * S n_reduced x n_reduced row-major, both triangles filled; b n_reduced */
 int rcc_ba_get_reduced_system(rcc_ba_problem* p, double* S, double* b);
+/* a rectangular window of the same matrix without materialising it on the host (n_reduced = 30 009 is 7.2 GB):
+ * out[i * n_cols + j] = S[row0 + i][col0 + j] for 0 <= row0 + i < n_reduced and 0 <= col0 + j <= n_reduced, where
+ * column n_reduced is the right-hand side b (so a window that ends at col0 + n_cols == n_reduced + 1 carries b) */
+int rcc_ba_get_reduced_block(rcc_ba_problem* p, int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols, double* out);
 /* last step: d_e n_e x 6, d_f n_f x 6, d_shared n_shared */
 int rcc_ba_get_step(rcc_ba_problem* p, double* d_e, double* d_f, double* d_shared);
 

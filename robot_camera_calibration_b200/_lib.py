@@ -84,6 +84,7 @@ SIGNATURES = {
     "rcc_ba_get_dims": (C.c_int, [_H, C.POINTER(Dims)]),
     "rcc_ba_get_normal_blocks": (C.c_int, [_H] + [c_double_p] * 9),
     "rcc_ba_get_reduced_system": (C.c_int, [_H, c_double_p, c_double_p]),
+    "rcc_ba_get_reduced_block": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
     "rcc_ba_get_step": (C.c_int, [_H, c_double_p, c_double_p, c_double_p]),
     "rcc_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "rcc_ba_comm_init": (C.c_int, [_H, C.c_char_p, C.c_int32, C.c_int32]),

@@ -169,10 +169,19 @@ class Problem:
         rig = self._blocks[0][0].rig
         views, markers, cams = {}, {}, {}
         vi, mi, ci, px, sizes = [], [], [], [], {}
+        seen = {}     # id(array) -> camera key: one Ceres parameter block must belong to exactly one GPU camera
         for cost, intr, dist, view, marker, ext in self._blocks:
+            if cost.rig != rig:
+                raise NotImplementedError("rig and single-camera cost functions cannot be mixed in one problem")
             v = views.setdefault(id(view), (len(views), view))[0]
             m = markers.setdefault(id(marker), (len(markers), marker))[0]
             key = (id(intr), id(dist), id(ext) if ext is not None else 0)
+            for arr in (intr, dist, ext):
+                if arr is not None and seen.setdefault(id(arr), key) != key:
+                    raise NotImplementedError(
+                        "an intrinsics / distortion / extrinsics array is shared by residual blocks whose other "
+                        "camera blocks differ: the GPU camera record is (intr, dist, ext) as a unit, so the shared "
+                        "array would be optimised as several independent copies")
             c = cams.setdefault(key, (len(cams), intr, dist, ext))[0]
             if sizes.setdefault(m, cost.tag_size) != cost.tag_size:
                 raise ValueError("one marker was given two different tag sizes")

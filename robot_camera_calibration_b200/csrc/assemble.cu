@@ -266,11 +266,8 @@ static void launch_assemble_t(const AssembleArgs& a, cudaStream_t s) {
   if (a.n_chunks == 0) return;
   const size_t smem = PG::WARPS * WarpSmem<RIG, EPASS>::TOTAL * sizeof(double);
   auto k = assemble_kernel<RIG, EPASS, OWN_IS_VIEW, LOSS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RCC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static SmemOptIn optin;   // one per template instantiation
+  optin.ensure(k, smem);
   const int grid = ceil_div(a.n_chunks, PG::WARPS);
   k<<<grid, PG::WARPS * 32, smem, s>>>(a);
   RCC_CUDA(cudaGetLastError());

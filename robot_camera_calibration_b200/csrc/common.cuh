@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <atomic>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -66,6 +67,23 @@ struct DBuf {
   }
   void zero(cudaStream_t s) {
     if (n) RCC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per device, and a process may hold
+// handles on several devices (include/rcc_ba.h: "distinct handles are independent"), so the opt-in is
+// remembered per (call site, current device); thread-safe.
+struct SmemOptIn {
+  std::atomic<uint64_t> done[4] = {};   // bit d of word d/64: set on device d
+  template <typename K>
+  void ensure(K kernel, size_t smem) {
+    int dev = 0;
+    RCC_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    std::atomic<uint64_t>& w = done[(dev >> 6) & 3];
+    if (w.load(std::memory_order_acquire) & bit) return;
+    RCC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    w.fetch_or(bit, std::memory_order_release);
   }
 };
 

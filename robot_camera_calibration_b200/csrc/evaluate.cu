@@ -317,11 +317,8 @@ template <bool RIG, bool OWN_IS_VIEW>
 static void launch_materialise_t(const EvalArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)MAT_WARPS * MatSmem<RIG>::TOTAL * sizeof(double);
   auto k = materialise_kernel<RIG, OWN_IS_VIEW>;
-  static bool attr = false;
-  if (!attr) {
-    RCC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static SmemOptIn optin;
+  optin.ensure(k, smem);
   k<<<ceil_div(a.n_chunks, MAT_WARPS), MAT_WARPS * 32, smem, s>>>(a);
   RCC_CUDA(cudaGetLastError());
 }

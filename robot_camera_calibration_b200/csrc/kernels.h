@@ -266,6 +266,6 @@ void launch_permute_pixels(const double* src, const int32_t* orig, double* dst, 
 // write a scratch buffer (L2 flush)
 void launch_fill(double* p, int64_t n, double v, cudaStream_t s);
 // FP64 FMA throughput microbenchmark kernel; returns number of FMAs issued
-double launch_fp64_peak(int iters, cudaStream_t s);
+double launch_fp64_peak(int iters, double* sink, cudaStream_t s);
 
 }  // namespace rcc

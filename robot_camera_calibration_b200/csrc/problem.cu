@@ -122,7 +122,15 @@ typedef rcc_ba_problem P_t;
       throw Error(RCC_SOLVER_ERROR, std::string(#expr) + ": cusolver status " + std::to_string((int)_r)); \
   } while (0)
 
-static void sync(P_t* P) { RCC_CUDA(cudaStreamSynchronize(P->stream)); }
+static void sync(P_t* P) {
+  RCC_CUDA(cudaStreamSynchronize(P->stream));
+  if (P->pix_pending) {
+    // a piecewise rcc_ba_update_pixels is still reading the caller's buffer on the copy streams and the main
+    // stream has not joined them yet: the header promises the buffer is free once a getter / synchronize returns
+    RCC_CUDA(cudaStreamSynchronize(P->side_stream));
+    RCC_CUDA(cudaStreamSynchronize(P->side_stream2));
+  }
+}
 
 // caller buffer -> internal pinned slot (waits for the slot's previous H2D copy, normally long done)
 enum { HS_VIEWS = 0, HS_MARKERS, HS_INTR, HS_DIST, HS_EXT };
@@ -690,8 +698,9 @@ static void do_candidate_cost(P_t* P) {
   }
   {
     Scoped t(P, ST_COST, 2);
-    RCC_CUDA(cudaMemsetAsync(P->fail_flag.p, 0, sizeof(int32_t), P->stream));
     EvalArgs a = eval_args(P, true);
+    a.fail_flag = P->fail_flag.p + 1;   // slot 1: candidate point (slot 0 keeps the linearisation point's flag)
+    RCC_CUDA(cudaMemsetAsync(a.fail_flag, 0, sizeof(int32_t), P->stream));
     launch_cost(P->rig, a, P->stream);
     launch_sum(P->cost_partials.p, eval_grid(P->n_obs), P->stats.p + SX_CAND2, 1.0, P->stream);
   }
@@ -699,15 +708,15 @@ static void do_candidate_cost(P_t* P) {
     Scoped t(P, ST_ALLREDUCE, 2);
     RCC_NCCL(ncclAllReduce(P->stats.p + SX_MCC_E, P->stats.p + SX_MCC_E, 4, ncclDouble, ncclSum, P->comm, P->stream));
     RCC_NCCL(ncclAllReduce(P->stats.p + SX_GMAX_E, P->stats.p + SX_GMAX_E, 1, ncclDouble, ncclMax, P->comm, P->stream));
-    // the fail flag must be seen by every rank
-    RCC_NCCL(ncclAllReduce(P->fail_flag.p, P->fail_flag.p, 1, ncclInt32, ncclMax, P->comm, P->stream));
+    // both fail flags (linearisation point, candidate point) must be seen by every rank
+    RCC_NCCL(ncclAllReduce(P->fail_flag.p, P->fail_flag.p, 2, ncclInt32, ncclMax, P->comm, P->stream));
   }
   P->cand_ready = true;
 }
 
 struct StepScalars {
   double mcc, step_norm, x_norm, cand_cost, cur_cost, gmax;
-  int potrf_info, fail;
+  int potrf_info, fail, fail_lin;   // fail: candidate point; fail_lin: the point the system was linearised at
 };
 
 static StepScalars read_step_scalars(P_t* P) {
@@ -715,7 +724,7 @@ static StepScalars read_step_scalars(P_t* P) {
   RCC_CUDA(cudaMemcpyAsync(h, P->stats.p, SX_N * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
   int* hi = reinterpret_cast<int*>(h + 16);
   RCC_CUDA(cudaMemcpyAsync(hi, P->dev_info.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
-  RCC_CUDA(cudaMemcpyAsync(hi + 2, P->fail_flag.p, sizeof(int), cudaMemcpyDeviceToHost, P->stream));
+  RCC_CUDA(cudaMemcpyAsync(hi + 2, P->fail_flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, P->stream));
   sync(P);
   StepScalars s;
   s.mcc = h[SX_MCC_E] + h[SX_MCC_F];
@@ -725,7 +734,8 @@ static StepScalars read_step_scalars(P_t* P) {
   s.cur_cost = 0.5 * h[SX_COST2];
   s.gmax = std::max(h[SX_GMAX_E], h[SX_GMAX_F]);
   s.potrf_info = hi[0];
-  s.fail = hi[2];
+  s.fail_lin = hi[2];
+  s.fail = hi[3];
   return s;
 }
 
@@ -768,6 +778,13 @@ static void do_solve(P_t* P, const rcc_lm_options& o, rcc_lm_summary& sum) {
     cost = s.cur_cost;
     if (it == 0) sum.initial_cost = cost;
     sum.final_gradient_max = s.gmax;
+    if (s.fail_lin || !std::isfinite(cost)) {
+      // the current point itself cannot be evaluated (corner at depth <= 0, non-finite residual): H and g are
+      // garbage, so stop -- Ceres returns FAILURE when the initial evaluation fails
+      if (o.verbose) fprintf(stderr, "[rcc_ba] it %3d evaluation failed at the linearisation point\n", it);
+      sum.termination = 4;
+      break;
+    }
     if (need_lin && s.gmax < o.gradient_tolerance) {
       sum.termination = 2;
       break;
@@ -936,7 +953,7 @@ int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
     P->delta_e.alloc((size_t)P->n_e * 6); P->delta_e.zero(s);
     P->bs_partials.alloc((size_t)P->n_e * 4);
     P->stats.alloc(16); P->stats.zero(s);
-    P->fail_flag.alloc(1); P->fail_flag.zero(s);
+    P->fail_flag.alloc(4); P->fail_flag.zero(s);
     P->dev_info.alloc(2); P->dev_info.zero(s);
     P->scalar.alloc(8);
     RCC_SOLVER(cusolverDnCreate(&P->solver));
@@ -1168,7 +1185,8 @@ static int evaluate_impl(P_t* P, int want_j, double* cost, bool to_host, double*
     if (all || jm) { P->o_jm.ensure(n * 48); a.jac_marker = P->o_jm.p; }
     if (P->rig && (all || jx)) { P->o_jx.ensure(n * 48); a.jac_ext = P->o_jx.p; }
   }
-  RCC_CUDA(cudaMemsetAsync(P->fail_flag.p, 0, sizeof(int32_t), P->stream));
+  a.fail_flag = P->fail_flag.p + 2;   // slot 2: materialised evaluation
+  RCC_CUDA(cudaMemsetAsync(a.fail_flag, 0, sizeof(int32_t), P->stream));
   {
     Scoped t(P, ST_EVALUATE, 2);
     launch_evaluate(P->rig, want_j != 0, a, P->stream);
@@ -1187,7 +1205,7 @@ static int evaluate_impl(P_t* P, int want_j, double* cost, bool to_host, double*
   }
   if (cost || to_host) {
     RCC_CUDA(cudaMemcpyAsync(P->h_pinned, P->scalar.p, sizeof(double), cudaMemcpyDeviceToHost, P->stream));
-    RCC_CUDA(cudaMemcpyAsync(P->h_pinned + 1, P->fail_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, P->stream));
+    RCC_CUDA(cudaMemcpyAsync(P->h_pinned + 1, P->fail_flag.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, P->stream));
     sync(P);
     if (cost) *cost = P->h_pinned[0];
     fail = *reinterpret_cast<int32_t*>(P->h_pinned + 1);
@@ -1338,6 +1356,33 @@ int rcc_ba_get_reduced_system(rcc_ba_problem* P, double* S, double* b) {
   API_END(P)
 }
 
+int rcc_ba_get_reduced_block(rcc_ba_problem* P, int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols, double* out) {
+  API_BEGIN(P)
+  RCC_REQUIRE(P->schur_done, RCC_NOT_READY, "reduced system not available (call schur; solve_step overwrites it)");
+  const int n = P->n_red;
+  RCC_REQUIRE(out && row0 >= 0 && n_rows > 0 && row0 + n_rows <= n && col0 >= 0 && n_cols > 0 && col0 + n_cols <= n + 1,
+              RCC_BAD_ARG, "window outside the reduced system");
+  // the buffer holds the upper triangle (+ rhs in column n): fetch the window and its mirror image
+  std::vector<double> a((size_t)n_rows * n_cols), b;
+  RCC_CUDA(cudaMemcpy2DAsync(a.data(), (size_t)n_cols * sizeof(double), P->S.p + (size_t)row0 * P->ld + col0,
+                             (size_t)P->ld * sizeof(double), (size_t)n_cols * sizeof(double), n_rows,
+                             cudaMemcpyDeviceToHost, P->stream));
+  const int mc = std::min(n_cols, n - col0);   // mirrored part: columns < n only
+  if (mc > 0) {
+    b.resize((size_t)mc * n_rows);
+    RCC_CUDA(cudaMemcpy2DAsync(b.data(), (size_t)n_rows * sizeof(double), P->S.p + (size_t)col0 * P->ld + row0,
+                               (size_t)P->ld * sizeof(double), (size_t)n_rows * sizeof(double), mc,
+                               cudaMemcpyDeviceToHost, P->stream));
+  }
+  sync(P);
+  for (int i = 0; i < n_rows; ++i)
+    for (int j = 0; j < n_cols; ++j) {
+      const int r = row0 + i, c = col0 + j;
+      out[(size_t)i * n_cols + j] = (c >= r) ? a[(size_t)i * n_cols + j] : b[(size_t)j * n_rows + i];
+    }
+  API_END(P)
+}
+
 int rcc_ba_get_step(rcc_ba_problem* P, double* d_e, double* d_f, double* d_shared) {
   API_BEGIN(P)
   RCC_REQUIRE(P->step_ready, RCC_NOT_READY, "solve_step has not been called");
@@ -1431,11 +1476,13 @@ int rcc_fp64_peak_tflops(int32_t device, double* tflops) {
     cudaEvent_t a, b;
     RCC_CUDA(cudaEventCreate(&a));
     RCC_CUDA(cudaEventCreate(&b));
-    launch_fp64_peak(200, s);
+    double* sink = nullptr;   // per call and per device (a process-wide pointer would belong to one device only)
+    RCC_CUDA(cudaMalloc(&sink, 8));
+    launch_fp64_peak(200, sink, s);
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
       RCC_CUDA(cudaEventRecord(a, s));
-      const double fmas = launch_fp64_peak(4000, s);
+      const double fmas = launch_fp64_peak(4000, sink, s);
       RCC_CUDA(cudaEventRecord(b, s));
       RCC_CUDA(cudaStreamSynchronize(s));
       float ms = 0.f;
@@ -1445,6 +1492,7 @@ int rcc_fp64_peak_tflops(int32_t device, double* tflops) {
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     cudaStreamDestroy(s);
+    cudaFree(sink);
     *tflops = best;
   } catch (const Error& e) {
     g_create_error = e.what();

@@ -472,11 +472,8 @@ void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s) {
   if (a.n_f == 0) return;
   RCC_REQUIRE(a.tile_w == 32, RCC_BAD_ARG, "schur_syrk: tile_ptr granularity must be 32");
   const size_t smem = (size_t)(SY_WARPS * SY_SUB * 36 + 2 * SY_BATCH * 36) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    RCC_CUDA(cudaFuncSetAttribute(schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static SmemOptIn optin;
+  optin.ensure(schur_syrk_kernel, smem);
   if (a.n_ctas > 0) schur_syrk_kernel<<<a.n_ctas, SY_WARPS * 32, smem, s>>>(a);
   RCC_CUDA(cudaGetLastError());
 }
@@ -805,11 +802,9 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) 
   const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
   if (s == 12345.678) out[0] = s;
 }
-static double* g_peak_sink = nullptr;
-double launch_fp64_peak(int iters, cudaStream_t s) {
-  if (!g_peak_sink) RCC_CUDA(cudaMalloc(&g_peak_sink, 8));
+double launch_fp64_peak(int iters, double* sink, cudaStream_t s) {
   const int grid = NUM_SMS_B200 * 8;
-  fp64_peak_kernel<<<grid, 256, 0, s>>>(g_peak_sink, iters);
+  fp64_peak_kernel<<<grid, 256, 0, s>>>(sink, iters);   // sink: 8 bytes on the current device, never written
   RCC_CUDA(cudaGetLastError());
   return (double)grid * 256.0 * (double)iters * 64.0;  // FMAs
 }

@@ -124,13 +124,19 @@ def read_camera_yaml(path):
     return np.array([K[0], K[4], K[2], K[5]]), np.array(d)
 
 
-def read_dataset(directory):
+def read_dataset(directory, intr=None, dist=None):
     """Read targets.yaml + detections_*.yaml (+ camera.yaml) into a Scene.
+    The intrinsics come from camera.yaml unless `intr` (fx fy cx cy) and `dist` (k1 k2 p1 p2 k3) are given;
+    a dataset with neither is an error (the reference logs ROS_ERROR when the intrinsics are not loaded,
+    camera_pose.cpp:66-67 -- optimising from made-up intrinsics would silently overwrite good files).
     Frames without a `world_T_camera` stanza (never referenced by
     camera_pose_node, camera_pose.cpp:278-281) and tags missing from targets.yaml
     are skipped.  Returns (scene, tag_ids, frame_numbers)."""
     with open(os.path.join(directory, "targets.yaml")) as f:
-        targets = yaml.safe_load(f)["targets"] or []
+        targets = (yaml.safe_load(f) or {}).get("targets") or []
+    if not targets:
+        raise ValueError(f"{directory}/targets.yaml lists no targets: nothing defines the world frame "
+                         "(camera_pose.cpp:71-80 makes the first tag of frame 0 the world tag)")
     tag_ids = np.array([int(t["targetID"]) for t in targets])
     index_of = {int(t): i for i, t in enumerate(tag_ids)}
     markers = np.array([list(t["world_T_target"]["rotation"]) + list(t["world_T_target"]["translation"])
@@ -157,7 +163,13 @@ def read_dataset(directory):
             mi.append(index_of[tid])
             px.append([float(c[k][a]) for k in range(4) for a in range(2)])
     cam = os.path.join(directory, "camera.yaml")
-    intr, dist = read_camera_yaml(cam) if os.path.exists(cam) else (np.array([600.0, 600.0, 320.0, 240.0]), np.zeros(5))
+    if intr is not None and dist is not None:
+        intr, dist = np.asarray(intr, dtype=np.float64), np.asarray(dist, dtype=np.float64)
+    elif os.path.exists(cam):
+        intr, dist = read_camera_yaml(cam)
+    else:
+        raise FileNotFoundError(f"{cam} not found and no intr/dist given: the camera intrinsics are required "
+                                "(camera_pose.cpp:59-67)")
     scene = Scene(model="single", intr=intr.reshape(1, 4), dist=dist.reshape(1, 5), ext=np.zeros((1, 6)),
                   views=np.array(views, dtype=np.float64).reshape(-1, 6), markers=markers, sizes=sizes,
                   view_idx=np.array(vi, dtype=np.int32), marker_idx=np.array(mi, dtype=np.int32),
@@ -180,10 +192,11 @@ def write_results(directory, scene, tag_ids, frames, precision=None):
             f.write(head + world_T_camera_text(scene.views[v, 0:3], scene.views[v, 3:6], precision))
 
 
-def optimise_directory(directory, device=0, refine_intrinsics=True, precision=None, **lm_options):
+def optimise_directory(directory, device=0, refine_intrinsics=True, precision=None, intr=None, dist=None,
+                       **lm_options):
     """Milestone 3: detections/ -> GPU bundle adjustment -> detections/ (same formats)."""
     from .problem import BAProblem
-    scene, tag_ids, frames = read_dataset(directory)
+    scene, tag_ids, frames = read_dataset(directory, intr=intr, dist=dist)
     scene.const_intr[:] = not refine_intrinsics
     scene.const_dist[:] = not refine_intrinsics
     with BAProblem.from_scene(scene, device=device) as p:

@@ -213,6 +213,12 @@ class BAProblem:
         self._check(self.lib.rcc_ba_get_reduced_system(self.h, _dp(S), _dp(b)))
         return S, b
 
+    def reduced_block(self, row0, n_rows, col0, n_cols):
+        """S[row0:row0+n_rows, col0:col0+n_cols] (column n_reduced = the right-hand side b)."""
+        out = np.empty((n_rows, n_cols))
+        self._check(self.lib.rcc_ba_get_reduced_block(self.h, int(row0), int(n_rows), int(col0), int(n_cols), _dp(out)))
+        return out
+
     def solve_step(self):
         mcc, sn, xn = C.c_double(), C.c_double(), C.c_double()
         self._check(self.lib.rcc_ba_solve_step(self.h, C.byref(mcc), C.byref(sn), C.byref(xn)))

@@ -157,10 +157,79 @@ def _look_at(cam_pos, target, roll):
     return R @ Rz
 
 
+def _wall_views(rng, n, wall_w, wall_h, d_mean, T0inv):
+    """n views looking at random points of the wall from d in [0.7, 1.3] d_mean (tags face -z of the wall
+    frame towards the cameras: wall normal is +z, the camera sits at negative z looking towards +z)."""
+    tgt = np.stack([rng.uniform(-0.5, 0.5, n) * wall_w * 0.9,
+                    rng.uniform(-0.5, 0.5, n) * wall_h * 0.9,
+                    np.zeros(n)], -1)
+    dist_cam = rng.uniform(0.7, 1.3, n) * d_mean
+    off = rng.normal(0, 0.25, (n, 2))
+    cam_pos = tgt + np.stack([off[:, 0] * dist_cam, off[:, 1] * dist_cam,
+                              -dist_cam * np.sqrt(np.maximum(0.2, 1 - (off ** 2).sum(-1)))], -1)
+    Rwc = _look_at(cam_pos, tgt, rng.normal(0, 0.2, n))
+    views_wall = np.concatenate([rotation_to_rvec(Rwc), cam_pos], -1)
+    return compose(np.broadcast_to(T0inv, views_wall.shape), views_wall)
+
+
+def _chunk_observations(rng, v0, views_c, markers_t, sizes, intr_t, dist_t, ext_t, model, n_cam, visibility,
+                        W, Himg, tag_size, dtype_idx):
+    """Observation blocks of the views views_c (global view numbers v0, v0+1, ...): every tag whose 4 corners
+    project inside the image with positive depth, thinned at random to the requested visibility."""
+    n_markers = len(markers_t)
+    nv = len(views_c)
+    m_all = np.arange(n_markers)
+    vi_l, mi_l, ci_l, px_l = [], [], [], []
+    Rv = rodrigues_np(views_c[:, 0:3])                                       # (nv,3,3)
+    # marker centres in the view/body frame: R^T (t_m - t_v)   (cheap conservative prefilter)
+    ctr = np.einsum('vji,vmj->vmi', Rv, markers_t[None, :, 3:6] - views_c[:, None, 3:6])
+    for c in range(n_cam):
+        pc = ctr
+        if model == "rig":
+            Rx = rodrigues_np(ext_t[c, 0:3])
+            pc = (ctr - ext_t[c, 3:6]) @ Rx                                   # Rx^T (p - t_x)
+        zc = np.maximum(pc[..., 2], 1e-9)
+        margin = 0.35 * max(W, Himg) + intr_t[c, 0] * tag_size / zc          # distortion + tag extent
+        cand = ((pc[..., 2] > 0.05)
+                & (np.abs(intr_t[c, 0] * pc[..., 0] / zc + intr_t[c, 2] - W / 2) < W / 2 + margin)
+                & (np.abs(intr_t[c, 1] * pc[..., 1] / zc + intr_t[c, 3] - Himg / 2) < Himg / 2 + margin))
+        cv_, cm_ = np.nonzero(cand)
+        uv_c, Z_c = project(model, np.broadcast_to(intr_t[c], (len(cv_), 4)),
+                            np.broadcast_to(dist_t[c], (len(cv_), 5)),
+                            np.broadcast_to(ext_t[c], (len(cv_), 6)),
+                            views_c[cv_], markers_t[cm_], sizes[cm_])
+        ok_c = ((Z_c > 0.1).all(-1) & (uv_c[..., 0] >= 0).all(-1) & (uv_c[..., 0] < W).all(-1)
+                & (uv_c[..., 1] >= 0).all(-1) & (uv_c[..., 1] < Himg).all(-1))
+        # scatter back to the dense (view, marker) grid the thinning below works on
+        vv = np.repeat(np.arange(v0, v0 + nv), n_markers)
+        mm = np.tile(m_all, nv)
+        ok = np.zeros(nv * n_markers, bool)
+        flat = cv_ * n_markers + cm_
+        ok[flat[ok_c]] = True
+        # thin to the requested visibility
+        n_keep = int(round(visibility * n_markers))
+        okm = ok.reshape(nv, n_markers)
+        cnt = okm.sum(1)
+        over = np.nonzero(cnt > n_keep)[0]
+        if len(over):
+            score = rng.random((nv, n_markers))
+            score[~okm] = 2.0
+            kth = np.partition(score[over], n_keep - 1, axis=1)[:, n_keep - 1]
+            okm[over] &= score[over] <= kth[:, None]
+        ok = okm.ravel()
+        sel = np.nonzero(ok)[0]
+        vi_l.append(vv[sel].astype(dtype_idx))
+        mi_l.append(mm[sel].astype(dtype_idx))
+        ci_l.append(np.full(len(sel), c, dtype_idx))
+        pos = np.searchsorted(flat, sel)                      # flat is sorted (np.nonzero order)
+        px_l.append(uv_c[pos].reshape(-1, 8))
+    return np.concatenate(vi_l), np.concatenate(mi_l), np.concatenate(ci_l), np.concatenate(px_l)
+
+
 def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
                tag_size=0.1, pixel_noise=0.3, image_size=(640, 480),
                perturb=(0.02, 0.02, 0.01), round_pixels=False, chunk_views=256,
-               name="", dtype_idx=np.int32, view_seed=None):
+               name="", dtype_idx=np.int32, view_seed=None, blocked=False, view_range=None, threads=None):
     """Generate a synthetic marker scene.
 
     visibility : target fraction of tags seen per view (per camera); the wall
@@ -170,6 +239,11 @@ def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
                  generator seeded (seed, view_seed) while cameras and tags only
                  depend on `seed` -- weak-scaling shards share one tag cloud.
     round_pixels: truncate pixels to int like corner_detections.cpp:53-54.
+    blocked    : every chunk of `chunk_views` views draws from its own random stream
+                 (seed, chunk number): chunks are generated by `threads` host threads, and
+                 `view_range=(lo, hi)` (multiples of chunk_views) yields exactly the views lo..hi-1 of the
+                 full scene, renumbered from 0 -- the strong-scaling shards of one fixed problem.
+                 The default (False) keeps the single sequential stream.
     """
     rng = np.random.default_rng(seed)
     W, Himg = image_size
@@ -213,92 +287,63 @@ def make_scene(n_markers, n_views, visibility, n_cam=1, model="single", seed=0,
     markers_t = compose(np.broadcast_to(T0inv, markers_t.shape), markers_t)
     markers_t[0] = 0.0
     sizes = np.full(n_markers, tag_size)
+    s_r, s_t, s_i = perturb
+    obs_args = (markers_t, sizes, intr_t, dist_t, ext_t, model, n_cam, visibility, W, Himg, tag_size, dtype_idx)
 
-    if view_seed is not None:
-        # initial guesses of the shared blocks must not depend on the shard either
+    if blocked:
+        # ---- one random stream per chunk of views: parallel, and any aligned view range on its own
+        lo, hi = (0, n_views) if view_range is None else view_range
+        if lo % chunk_views or not (0 <= lo <= hi <= n_views):
+            raise ValueError("view_range must start on a multiple of chunk_views and lie inside 0..n_views")
         rng_shared = np.random.default_rng([seed, 7919])
-        rng = np.random.default_rng([seed, int(view_seed)])
-    else:
-        rng_shared = None
-    # ---- views: look at a random point of the wall from d in [0.7,1.3] d_mean
-    # (tags face -z of the wall frame towards the cameras: wall normal is +z,
-    #  camera sits at negative z looking towards +z)
-    tgt = np.stack([rng.uniform(-0.5, 0.5, n_views) * wall_w * 0.9,
-                    rng.uniform(-0.5, 0.5, n_views) * wall_h * 0.9,
-                    np.zeros(n_views)], -1)
-    dist_cam = rng.uniform(0.7, 1.3, n_views) * d_mean
-    off = rng.normal(0, 0.25, (n_views, 2))
-    cam_pos = tgt + np.stack([off[:, 0] * dist_cam, off[:, 1] * dist_cam,
-                              -dist_cam * np.sqrt(np.maximum(0.2, 1 - (off ** 2).sum(-1)))], -1)
-    Rwc = _look_at(cam_pos, tgt, rng.normal(0, 0.2, n_views))
-    views_wall = np.concatenate([rotation_to_rvec(Rwc), cam_pos], -1)
-    views_t = compose(np.broadcast_to(T0inv, views_wall.shape), views_wall)
+        vs = [] if view_seed is None else [int(view_seed)]
 
-    # ---- observations (chunked over views so 10k x 5k scenes stay in memory)
-    vi_l, mi_l, ci_l, px_l = [], [], [], []
-    m_all = np.arange(n_markers)
-    for v0 in range(0, n_views, chunk_views):
-        v1 = min(n_views, v0 + chunk_views)
-        nv = v1 - v0
-        Rv = rodrigues_np(views_t[v0:v1, 0:3])                                   # (nv,3,3)
-        # marker centres in the view/body frame: R^T (t_m - t_v)   (cheap conservative prefilter)
-        ctr = np.einsum('vji,vmj->vmi', Rv, markers_t[None, :, 3:6] - views_t[v0:v1, None, 3:6])
-        for c in range(n_cam):
-            pc = ctr
-            if model == "rig":
-                Rx = rodrigues_np(ext_t[c, 0:3])
-                pc = (ctr - ext_t[c, 3:6]) @ Rx                                   # Rx^T (p - t_x)
-            zc = np.maximum(pc[..., 2], 1e-9)
-            margin = 0.35 * max(W, Himg) + intr_t[c, 0] * tag_size / zc          # distortion + tag extent
-            cand = ((pc[..., 2] > 0.05)
-                    & (np.abs(intr_t[c, 0] * pc[..., 0] / zc + intr_t[c, 2] - W / 2) < W / 2 + margin)
-                    & (np.abs(intr_t[c, 1] * pc[..., 1] / zc + intr_t[c, 3] - Himg / 2) < Himg / 2 + margin))
-            cv_, cm_ = np.nonzero(cand)
-            vv_c, mm_c = (cv_ + v0), cm_
-            uv_c, Z_c = project(model, np.broadcast_to(intr_t[c], (len(vv_c), 4)),
-                                np.broadcast_to(dist_t[c], (len(vv_c), 5)),
-                                np.broadcast_to(ext_t[c], (len(vv_c), 6)),
-                                views_t[vv_c], markers_t[mm_c], sizes[mm_c])
-            ok_c = ((Z_c > 0.1).all(-1) & (uv_c[..., 0] >= 0).all(-1) & (uv_c[..., 0] < W).all(-1)
-                    & (uv_c[..., 1] >= 0).all(-1) & (uv_c[..., 1] < Himg).all(-1))
-            # scatter back to the dense (view, marker) grid the thinning below works on
-            vv = np.repeat(np.arange(v0, v1), n_markers)
-            mm = np.tile(m_all, nv)
-            ok = np.zeros(nv * n_markers, bool)
-            flat = cv_ * n_markers + cm_
-            ok[flat[ok_c]] = True
-            uv = None
-            uv_lookup = (flat, uv_c)
-            # thin to the requested visibility
-            n_keep = int(round(visibility * n_markers))
-            okm = ok.reshape(nv, n_markers)
-            cnt = okm.sum(1)
-            over = np.nonzero(cnt > n_keep)[0]
-            if len(over):
-                score = rng.random((nv, n_markers))
-                score[~okm] = 2.0
-                kth = np.partition(score[over], n_keep - 1, axis=1)[:, n_keep - 1]
-                okm[over] &= score[over] <= kth[:, None]
-            ok = okm.ravel()
-            sel = np.nonzero(ok)[0]
-            vi_l.append(vv[sel].astype(dtype_idx))
-            mi_l.append(mm[sel].astype(dtype_idx))
-            ci_l.append(np.full(len(sel), c, dtype_idx))
-            pos = np.searchsorted(uv_lookup[0], sel)          # flat is sorted (np.nonzero order)
-            px_l.append(uv_lookup[1][pos].reshape(-1, 8))
-    view_idx = np.concatenate(vi_l)
-    marker_idx = np.concatenate(mi_l)
-    cam_idx = np.concatenate(ci_l)
-    pixels = np.concatenate(px_l)
-    pixels = pixels + rng.normal(0, pixel_noise, pixels.shape)
+        def one(v0):
+            r = np.random.default_rng([seed, 104729, v0 // chunk_views] + vs)
+            v1 = min(hi, v0 + chunk_views, n_views)
+            vt = _wall_views(r, v1 - v0, wall_w, wall_h, d_mean, T0inv)
+            vi, mi, ci, px = _chunk_observations(r, v0 - lo, vt, *obs_args)
+            px = px + r.normal(0, pixel_noise, px.shape)
+            v0g = vt + np.concatenate([r.normal(0, s_r, (v1 - v0, 3)), r.normal(0, s_t, (v1 - v0, 3))], -1)
+            return vt, v0g, vi, mi, ci, px
+
+        starts = list(range(lo, hi, chunk_views))
+        if threads is None:
+            import os
+            threads = min(len(os.sched_getaffinity(0)), 16)
+        if threads > 1 and len(starts) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                parts = list(ex.map(one, starts))
+        else:
+            parts = [one(v0) for v0 in starts]
+        views_t = np.concatenate([p[0] for p in parts]) if parts else np.zeros((0, 6))
+        views0 = np.concatenate([p[1] for p in parts]) if parts else np.zeros((0, 6))
+        view_idx, marker_idx, cam_idx, pixels = (np.concatenate([p[k] for p in parts]) for k in (2, 3, 4, 5))
+        n_views = hi - lo
+        rs = rng_shared
+    else:
+        if view_range is not None:
+            raise ValueError("view_range needs blocked=True")
+        if view_seed is not None:
+            # initial guesses of the shared blocks must not depend on the shard either
+            rng_shared = np.random.default_rng([seed, 7919])
+            rng = np.random.default_rng([seed, int(view_seed)])
+        else:
+            rng_shared = None
+        views_t = _wall_views(rng, n_views, wall_w, wall_h, d_mean, T0inv)
+        # ---- observations (chunked over views so 10k x 5k scenes stay in memory)
+        parts = [_chunk_observations(rng, v0, views_t[v0:min(n_views, v0 + chunk_views)], *obs_args)
+                 for v0 in range(0, n_views, chunk_views)]
+        view_idx, marker_idx, cam_idx, pixels = (np.concatenate([p[k] for p in parts]) for k in range(4))
+        pixels = pixels + rng.normal(0, pixel_noise, pixels.shape)
+        # ---- initial guess = truth perturbed
+        views0 = views_t + np.concatenate([rng.normal(0, s_r, (n_views, 3)),
+                                           rng.normal(0, s_t, (n_views, 3))], -1)
+        rs = rng if rng_shared is None else rng_shared
     if round_pixels:
         pixels = np.trunc(pixels)               # int(...) truncation, corner_detections.cpp:53-54
 
-    # ---- initial guess = truth perturbed
-    s_r, s_t, s_i = perturb
-    views0 = views_t + np.concatenate([rng.normal(0, s_r, (n_views, 3)),
-                                       rng.normal(0, s_t, (n_views, 3))], -1)
-    rs = rng if rng_shared is None else rng_shared
     markers0 = markers_t + np.concatenate([rs.normal(0, s_r, (n_markers, 3)),
                                            rs.normal(0, s_t, (n_markers, 3))], -1)
     markers0[0] = 0.0

@@ -1,4 +1,12 @@
-"""GPU, BASELINE.json sizes: size-independent properties instead of a (too slow) dense oracle.
+"""GPU, BASELINE.json sizes.
+
+Oracle parity (test_blocks_and_reduced_system_match_the_oracle_at_baseline_sizes): K1 residuals / Jacobians, every
+K2 normal-equation block and sampled blocks of the K3 reduced system against ba_oracle (complex-step Jacobians,
+einsum / np.add.at sums, block Schur complement; tests/helpers.py, itself pinned to the dense oracle by
+tests/test_sparse_oracle.py) on cfg2 at full size and on cfg3 / cfg4 at their full tag counts with enough
+views for rows that span several chunks in both passes.
+
+Size-independent properties on top (the dense oracle cannot follow to 12 M blocks):
 
   * K1 (materialised Jacobians) and K2 (fused assembly) are two independent kernels: the
     gradient and the eliminated-block Hessians rebuilt on the host from K1's output must
@@ -14,7 +22,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import rel_fro
+from helpers import SparseSchurOracle, max_block_rel, oracle_blocks_sparse, rel_fro, to_oracle
 from robot_camera_calibration_b200.dist import shard_scene
 from robot_camera_calibration_b200.problem import BAProblem
 from robot_camera_calibration_b200.scenes import config_scene
@@ -104,3 +112,62 @@ def test_both_elimination_directions_give_the_same_step():
         dv, dm = (st["d_e"], st["d_f"]) if elim == "views" else (st["d_f"], st["d_e"])
         steps[elim] = np.concatenate([dv.ravel(), dm.ravel(), st["d_shared"]])
     assert rel_fro(steps["views"], steps["markers"]) < 1e-7
+
+
+# cfg2 in full; cfg3: all 2 000 tags x 4 cameras, 6 000 of the 20 000 body poses (every tag is then seen > 64 times
+# per camera: F-pass rows of several chunks); cfg4: all 5 000 tags, 400 of the 10 000 keyframes (~1 190 tags per
+# keyframe: E-pass rows of ~19 chunks, F-pass rows of 2)
+ORACLE_CASES = [(2, 1.0), (3, 0.3), (4, 0.04)]
+
+
+@pytest.mark.parametrize("cfg,scale", ORACLE_CASES)
+def test_blocks_and_reduced_system_match_the_oracle_at_baseline_sizes(cfg, scale):
+    s = config_scene(cfg, scale=scale, blocked=True)
+    p = to_oracle(s)
+    radius = 1e4
+    with BAProblem.from_scene(s, eliminate="views") as gp:      # the BASELINE configs eliminate the views
+        ev = gp.dims.eliminated_is_view == 1
+        n_f, ns, n = gp.dims.n_f, gp.dims.n_shared, gp.dims.n_reduced
+        out = gp.evaluate()
+        cost = gp.linearize()
+        nb = gp.normal_blocks()
+        gp.schur(radius)
+        ob = oracle_blocks_sparse(p, ev)
+        # ---- K1: residuals and Ceres-layout Jacobians of every observation block
+        assert max_block_rel(out["residuals"], ob["residuals"]) < 1e-9
+        for k, J in ob["jacobians"].items():
+            assert max_block_rel(out["jacobians"][k], J) < 1e-9, k
+        # ---- K2: every normal-equation block
+        assert abs(cost - ob["cost"]) <= 1e-11 * ob["cost"] and abs(out["cost"] - ob["cost"]) <= 1e-11 * ob["cost"]
+        for k in ("Hee", "ge", "Hes", "Hff", "gf", "Hfs", "W"):
+            assert max_block_rel(nb[k], ob[k], floor=1e-6 * np.abs(ob[k]).max()) < 1e-9, k
+        assert rel_fro(nb["Hss"], ob["Hss"]) < 1e-9 and rel_fro(nb["gs"], ob["gs"]) < 1e-9
+        # ---- K3: sampled blocks of the reduced system (kept x kept, border strip + rhs, shared corner)
+        so = SparseSchurOracle(p, ob, ev, radius)
+        rng = np.random.default_rng(cfg)
+        fi = s.marker_idx if ev else s.view_idx
+        ei = s.view_idx if ev else s.marker_idx
+        seen = np.unique(fi)
+        pairs = [(int(f), int(f)) for f in rng.choice(seen, 40)]
+        for e in rng.choice(np.unique(ei), 60):                   # co-visible pairs: both kept blocks share e
+            fs = np.unique(fi[ei == e])
+            a, b = rng.choice(fs, 2)
+            pairs.append((int(min(a, b)), int(max(a, b))))
+        pairs += [tuple(sorted(map(int, rng.choice(n_f, 2)))) for _ in range(40)]      # mostly never co-visible
+        pairs += [(0, n_f - 1), (n_f - 1, n_f - 1), (31, 32), (63, 64)]               # tile and strip boundaries
+        scale_s = max(np.abs(so.block(f, f)).max() for f, _ in pairs[:40])
+        worst = 0.0
+        for f, g in pairs:
+            want = so.block(f, g)
+            got = gp.reduced_block(6 * f, 6, 6 * g, 6)
+            worst = max(worst, np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-6 * scale_s))
+            if f != g:                                             # the mirrored window reads the same storage
+                assert np.array_equal(gp.reduced_block(6 * g, 6, 6 * f, 6), got.T)
+        assert worst < 1e-9, worst
+        for f in rng.choice(seen, 25):
+            want = so.border(int(f))
+            got = gp.reduced_block(6 * int(f), 6, 6 * n_f, ns + 1)
+            assert np.linalg.norm(got - want) <= 1e-9 * np.linalg.norm(want)
+        want = so.corner()
+        got = gp.reduced_block(6 * n_f, ns, 6 * n_f, ns + 1)
+        assert np.linalg.norm(got - want) <= 1e-9 * np.linalg.norm(want)
