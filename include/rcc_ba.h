@@ -119,6 +119,16 @@ int rcc_ba_set_observations(rcc_ba_problem* p, const int32_t* view_idx, const in
  * call the parameter setters BEFORE update_pixels so that they do not queue behind it.  Otherwise: one
  * H2D copy plus a device-side permutation into the sorted layouts. */
 int rcc_ba_update_pixels(rcc_ba_problem* p, const double* pixels /*n_obs_blocks x 8*/);
+/* Integer pixel corners -- the reference's own observation format: corner_detections.cpp:53-54 truncates the
+ * detector's corners to int before writing them, camera_pose.cpp:135-142 parses them back with .as<int>().
+ * 16 bits are lossless for any image up to 32 767 px; the conversion to FP64 happens on the device, so an update
+ * ships 16 bytes per tag over PCIe instead of 64 and the results are bit-identical to the FP64 entry points
+ * fed with the same integers.  Same ordering / asynchrony contract as rcc_ba_update_pixels. */
+int rcc_ba_set_observations_i16(rcc_ba_problem* p, const int32_t* view_idx, const int32_t* marker_idx,
+                                const int32_t* cam_idx, const int16_t* pixels /*n_obs_blocks x 8*/);
+int rcc_ba_set_observations_i32(rcc_ba_problem* p, const int32_t* view_idx, const int32_t* marker_idx,
+                                const int32_t* cam_idx, const int32_t* pixels /*n_obs_blocks x 8*/);
+int rcc_ba_update_pixels_i16(rcc_ba_problem* p, const int16_t* pixels /*n_obs_blocks x 8*/);
 /* hold a parameter block constant (the gauge: world tag, camera_pose.cpp:71-80) */
 int rcc_ba_set_constant(rcc_ba_problem* p, int32_t block_kind, int32_t index, int32_t is_constant);
 

@@ -7,12 +7,20 @@ import cv2
 import numpy as np
 
 
+POLISH = False   # True: run OpenCV's own LM (solvePnPRefineLM) to a tight TermCriteria after the stock call
+
+
 def tag_T_cam_inverse(tag_size, pixels8, K, dist):
-    """cam_T_tag as 4x4 from cv2.solvePnP (camera_pose.cpp:146-170)."""
+    """cam_T_tag as 4x4 from cv2.solvePnP (camera_pose.cpp:146-170).  The stock call stops at OpenCV's default
+    tolerance (usually 1e-9 from the minimiser, occasionally 0.2 away along a flat depth direction); with
+    POLISH the same cost is minimised to convergence so that a tight comparison is meaningful."""
     h = tag_size / 2
     obj = np.array([[-h, -h, 0], [h, -h, 0], [h, h, 0], [-h, h, 0]], float)
     img = np.asarray(pixels8, float).reshape(4, 2)
     ok, rvec, tvec = cv2.solvePnP(obj, img, K, dist, flags=cv2.SOLVEPNP_ITERATIVE)
+    if POLISH:
+        rvec, tvec = cv2.solvePnPRefineLM(obj, img, K, dist, rvec, tvec,
+                                          criteria=(cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 1000, 1e-16))
     R, _ = cv2.Rodrigues(rvec)
     T = np.eye(4)
     T[:3, :3], T[:3, 3] = R, tvec.ravel()
@@ -24,7 +32,9 @@ def to_rt(T):
     return np.concatenate([r.ravel(), T[:3, 3]])
 
 
-def initialise(frames_pixels, intr, dist):
+def initialise(frames_pixels, intr, dist, polish=False):
+    global POLISH
+    POLISH = bool(polish)
     K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
     dist = np.asarray(dist, float)
     ids, sizes, trans = [], [], []

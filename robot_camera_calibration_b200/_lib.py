@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("RCC_BA_LIB") or os.path.join(HERE, "librcc_ba.so")   
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)
+c_int16_p = C.POINTER(C.c_int16)
 
 RCC_OK, RCC_BAD_ARG, RCC_CUDA_ERROR, RCC_NCCL_ERROR, RCC_EVAL_FAILED, RCC_NOT_SPD, RCC_NOT_READY, RCC_SOLVER_ERROR = range(8)
 STATUS_NAMES = ["RCC_OK", "RCC_BAD_ARG", "RCC_CUDA_ERROR", "RCC_NCCL_ERROR", "RCC_EVAL_FAILED", "RCC_NOT_SPD",
@@ -67,6 +68,9 @@ SIGNATURES = {
     "rcc_ba_set_marker_sizes": (C.c_int, [_H, c_double_p]),
     "rcc_ba_set_observations": (C.c_int, [_H, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
     "rcc_ba_update_pixels": (C.c_int, [_H, c_double_p]),
+    "rcc_ba_set_observations_i16": (C.c_int, [_H, c_int32_p, c_int32_p, c_int32_p, c_int16_p]),
+    "rcc_ba_set_observations_i32": (C.c_int, [_H, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
+    "rcc_ba_update_pixels_i16": (C.c_int, [_H, c_int16_p]),
     "rcc_ba_set_constant": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32]),
     "rcc_ba_set_loss": (C.c_int, [_H, C.c_int32, C.c_double]),
     "rcc_ba_get_intrinsics": (C.c_int, [_H, c_double_p, c_double_p]),

@@ -263,6 +263,8 @@ void launch_apply(const double* x, const double* d, double* out, int64_t n, cuda
 void launch_symmetrize(double* S, int32_t n, int32_t ld, cudaStream_t s);
 // gather pixels from caller order into a sorted order
 void launch_permute_pixels(const double* src, const int32_t* orig, double* dst, int64_t n, cudaStream_t s);
+// integer pixels -> FP64: dst[g] = (double) src[orig ? orig[g] : g]  for blocks g in [0, n)
+void launch_convert_pixels_i16(const int16_t* src, const int32_t* orig, double* dst, int64_t n, cudaStream_t s);
 // write a scratch buffer (L2 flush)
 void launch_fill(double* p, int64_t n, double v, cudaStream_t s);
 // FP64 FMA throughput microbenchmark kernel; returns number of FMAs issued

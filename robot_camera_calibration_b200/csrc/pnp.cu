@@ -182,12 +182,13 @@ __global__ void __launch_bounds__(128) pnp_kernel(int64_t n, const double* __res
     for (int a = 0; a < 6; ++a) { q[a] = p[a] + rhs[a]; dn += rhs[a] * rhs[a]; pn += p[a] * p[a]; }
     bool ok2;
     const double c2 = pnp_cost<false>(q, sh, hs, pix, nullptr, nullptr, &ok2);
-    if (ok2 && c2 < cost) {
+    // Accept on "not worse up to rounding": along the weakly determined depth direction of a small tag the cost is
+    // flat to 1e-16 relative while the step is still 1e-8, so convergence is declared on the step alone.
+    if (ok2 && c2 <= cost * (1.0 + 4e-16)) {
       for (int a = 0; a < 6; ++a) p[a] = q[a];
-      const double dc = cost - c2;
       cost = pnp_cost<true>(p, sh, hs, pix, H, g, &ok);
       lambda = fmax(lambda * 0.1, 1e-12);
-      if (dc <= 1e-16 * cost || dn <= 1e-24 * (pn + 1e-24)) break;
+      if (dn <= 1e-26 * (pn + 1e-26)) break;
     } else {
       lambda *= 10.0;
       if (lambda > 1e12) break;

@@ -847,6 +847,16 @@ static void do_solve(P_t* P, const rcc_lm_options& o, rcc_lm_summary& sum) {
 // ---------------------------------------------------------------------------
 // extern "C" boundary
 // ---------------------------------------------------------------------------
+template <typename T>
+static void set_observations_int(P_t* P, const int32_t* view_idx, const int32_t* marker_idx, const int32_t* cam_idx,
+                                 const T* pixels) {
+  RCC_REQUIRE(view_idx && marker_idx && pixels, RCC_BAD_ARG, "null pointer");
+  std::vector<double> px((size_t)P->n_obs * 8);     // one-time setup: widen on the host
+#pragma omp parallel for
+  for (int64_t i = 0; i < P->n_obs * 8; ++i) px[i] = (double)pixels[i];
+  build_indices(P, view_idx, marker_idx, cam_idx, px.data());
+}
+
 static thread_local std::string g_create_error;
 
 #define API_BEGIN(P)                                     \
@@ -1097,6 +1107,53 @@ int rcc_ba_update_pixels(rcc_ba_problem* P, const double* pixels) {
     P->pix_staging.upload(pixels, (size_t)P->n_obs * 8, P->stream);
     launch_permute_pixels(P->pix_staging.p, P->e_orig.p, P->e_pix.p, P->n_obs, P->stream);
     launch_permute_pixels(P->pix_staging.p, P->f_orig.p, P->f_pix.p, P->n_obs, P->stream);
+  }
+  P->linearized = P->schur_done = P->step_ready = P->cand_ready = false;
+  API_END(P)
+}
+
+int rcc_ba_set_observations_i16(rcc_ba_problem* P, const int32_t* view_idx, const int32_t* marker_idx,
+                                const int32_t* cam_idx, const int16_t* pixels) {
+  API_BEGIN(P)
+  set_observations_int(P, view_idx, marker_idx, cam_idx, pixels);
+  API_END(P)
+}
+
+int rcc_ba_set_observations_i32(rcc_ba_problem* P, const int32_t* view_idx, const int32_t* marker_idx,
+                                const int32_t* cam_idx, const int32_t* pixels) {
+  API_BEGIN(P)
+  set_observations_int(P, view_idx, marker_idx, cam_idx, pixels);
+  API_END(P)
+}
+
+int rcc_ba_update_pixels_i16(rcc_ba_problem* P, const int16_t* pixels) {
+  API_BEGIN(P)
+  RCC_REQUIRE(pixels, RCC_BAD_ARG, "null pointer");
+  RCC_REQUIRE(P->have_obs, RCC_NOT_READY, "set_observations has not been called");
+  P->pix_i16.ensure((size_t)P->n_obs * 8);
+  if (P->pix_identity) {
+    // same piecewise scheme as rcc_ba_update_pixels with a quarter of the bytes on the link: each piece is
+    // copied and widened to FP64 on its copy stream; the E pass of the piece starts when its event fires
+    Scoped t(P, ST_H2D, rcc_ba_problem::PIX_PIECES);
+    RCC_CUDA(cudaEventRecord(P->ev_fork, P->stream));
+    RCC_CUDA(cudaStreamWaitEvent(P->side_stream, P->ev_fork, 0));
+    RCC_CUDA(cudaStreamWaitEvent(P->side_stream2, P->ev_fork, 0));
+    for (int k = 0; k < rcc_ba_problem::PIX_PIECES; ++k) {
+      cudaStream_t cs = (k & 1) ? P->side_stream2 : P->side_stream;
+      const int64_t b0 = P->piece_block[k], b1 = P->piece_block[k + 1];
+      if (b1 > b0) {
+        RCC_CUDA(cudaMemcpyAsync(P->pix_i16.p + b0 * 8, pixels + b0 * 8, (size_t)(b1 - b0) * 8 * sizeof(int16_t),
+                                 cudaMemcpyHostToDevice, cs));
+        launch_convert_pixels_i16(P->pix_i16.p + b0 * 8, nullptr, P->e_pix.p + b0 * 8, b1 - b0, cs);
+      }
+      RCC_CUDA(cudaEventRecord(P->ev_piece[k], cs));
+    }
+    P->pix_pending = true;
+  } else {
+    Scoped t(P, ST_H2D, 2);
+    P->pix_i16.upload(pixels, (size_t)P->n_obs * 8, P->stream);
+    launch_convert_pixels_i16(P->pix_i16.p, P->e_orig.p, P->e_pix.p, P->n_obs, P->stream);
+    launch_convert_pixels_i16(P->pix_i16.p, P->f_orig.p, P->f_pix.p, P->n_obs, P->stream);
   }
   P->linearized = P->schur_done = P->step_ready = P->cand_ready = false;
   API_END(P)

@@ -74,6 +74,7 @@ struct rcc_ba_problem {
   // observation blocks, E-sorted and F-sorted
   rcc::DBuf<int32_t> e_own, e_oth, e_cam, e_orig, f_oth, f_orig, e_chunk_ptr, f_chunk_ptr;
   rcc::DBuf<double> e_pix, f_pix, pix_staging;
+  rcc::DBuf<int16_t> pix_i16;        // device staging of rcc_ba_update_pixels_i16
   rcc::DBuf<rcc::Chunk> e_chunks, f_chunks;
   rcc::DBuf<int32_t> cam_chunks_e, cam_ptr_e, cam_chunks_f, cam_ptr_f;
   rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, row_pos0, col_ptr, col_pair, tile_ptr, syrk_ctas, e_count;

@@ -779,6 +779,23 @@ void launch_permute_pixels(const double* src, const int32_t* orig, double* dst, 
   RCC_CUDA(cudaGetLastError());
 }
 
+// one thread per corner (2 x int16 = one 32-bit load, one 16-byte store): both sides coalesced
+__global__ void convert_pixels_i16_kernel(const int16_t* __restrict__ src, const int32_t* __restrict__ orig,
+                                          double* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 4) return;
+  const int64_t g = i >> 2;
+  const int q = (int)(i & 3);
+  const int64_t sg = orig ? (int64_t)orig[g] : g;
+  const short2 v = reinterpret_cast<const short2*>(src + sg * 8)[q];
+  reinterpret_cast<double2*>(dst + g * 8)[q] = make_double2((double)v.x, (double)v.y);
+}
+void launch_convert_pixels_i16(const int16_t* src, const int32_t* orig, double* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  convert_pixels_i16_kernel<<<ceil_div(n * 4, 256), 256, 0, s>>>(src, orig, dst, n);
+  RCC_CUDA(cudaGetLastError());
+}
+
 __global__ void fill_kernel(double* p, int64_t n, double v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }

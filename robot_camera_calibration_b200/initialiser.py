@@ -19,7 +19,7 @@ from . import _lib as L
 from .scenes import Scene, compose, invert
 
 
-def pnp_batch(intr, dist, sizes, pixels, guess=None, device=0, max_iterations=30):
+def pnp_batch(intr, dist, sizes, pixels, guess=None, device=0, max_iterations=100):
     """cam_T_tag (n,6) and final cost (n,) for n tags (4 corners each) on the GPU."""
     lib = L.load()
     sizes = np.ascontiguousarray(sizes, np.float64)

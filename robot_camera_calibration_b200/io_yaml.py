@@ -161,7 +161,7 @@ def read_dataset(directory, intr=None, dist=None):
             c = det["corners"]
             vi.append(v)
             mi.append(index_of[tid])
-            px.append([float(c[k][a]) for k in range(4) for a in range(2)])
+            px.append([c[k][a] for k in range(4) for a in range(2)])
     cam = os.path.join(directory, "camera.yaml")
     if intr is not None and dist is not None:
         intr, dist = np.asarray(intr, dtype=np.float64), np.asarray(dist, dtype=np.float64)
@@ -173,8 +173,19 @@ def read_dataset(directory, intr=None, dist=None):
     scene = Scene(model="single", intr=intr.reshape(1, 4), dist=dist.reshape(1, 5), ext=np.zeros((1, 6)),
                   views=np.array(views, dtype=np.float64).reshape(-1, 6), markers=markers, sizes=sizes,
                   view_idx=np.array(vi, dtype=np.int32), marker_idx=np.array(mi, dtype=np.int32),
-                  cam_idx=np.zeros(len(vi), dtype=np.int32), pixels=np.array(px, dtype=np.float64).reshape(-1, 8))
+                  cam_idx=np.zeros(len(vi), dtype=np.int32), pixels=_pixel_array(px))
     return scene, tag_ids, np.array(frames)
+
+
+def _pixel_array(px):
+    """Corner lists -> (N,8) array.  corner_detections.cpp:53-54 writes integer corners: those stay integers
+    (int16 when they fit) so that BAProblem ships 16 bytes per tag to the GPU; anything else is FP64."""
+    if px and all(isinstance(v, int) for row in px for v in row):
+        a = np.array(px, dtype=np.int64).reshape(-1, 8)
+        if a.min() >= -32768 and a.max() <= 32767:
+            return a.astype(np.int16)
+        return a.astype(np.int32)
+    return np.array(px, dtype=np.float64).reshape(-1, 8)
 
 
 def write_results(directory, scene, tag_ids, frames, precision=None):

@@ -121,13 +121,28 @@ class BAProblem:
         vi = np.ascontiguousarray(view_idx, dtype=np.int32)
         mi = np.ascontiguousarray(marker_idx, dtype=np.int32)
         ci = None if cam_idx is None else np.ascontiguousarray(cam_idx, dtype=np.int32)
-        px = _f64(pixels, (self.n_obs, 8))
         if len(vi) != self.n_obs or len(mi) != self.n_obs:
             raise ValueError("observation arrays do not match n_obs_blocks")
-        self._check(self.lib.rcc_ba_set_observations(self.h, _ip(vi), _ip(mi), _ip(ci), _dp(px)))
+        pixels = np.asarray(pixels)
+        if pixels.dtype == np.int16:        # the reference's integer corners (corner_detections.cpp:53-54)
+            px = np.ascontiguousarray(pixels).reshape(self.n_obs, 8)
+            rc = self.lib.rcc_ba_set_observations_i16(self.h, _ip(vi), _ip(mi), _ip(ci), px.ctypes.data_as(L.c_int16_p))
+        elif np.issubdtype(pixels.dtype, np.integer):
+            px = np.ascontiguousarray(pixels, dtype=np.int32).reshape(self.n_obs, 8)
+            rc = self.lib.rcc_ba_set_observations_i32(self.h, _ip(vi), _ip(mi), _ip(ci), _ip(px))
+        else:
+            px = _f64(pixels, (self.n_obs, 8))
+            rc = self.lib.rcc_ba_set_observations(self.h, _ip(vi), _ip(mi), _ip(ci), _dp(px))
+        self._check(rc)
         self._check(self.lib.rcc_ba_get_dims(self.h, C.byref(self.dims)))
 
     def update_pixels(self, pixels):
+        """FP64 pixels, or int16 (the reference's integer corners: a quarter of the bytes over PCIe)."""
+        pixels = np.asarray(pixels)
+        if pixels.dtype == np.int16:
+            px = np.ascontiguousarray(pixels).reshape(self.n_obs, 8)
+            self._check(self.lib.rcc_ba_update_pixels_i16(self.h, px.ctypes.data_as(L.c_int16_p)))
+            return
         px = _f64(pixels, (self.n_obs, 8))
         self._check(self.lib.rcc_ba_update_pixels(self.h, _dp(px)))
 

@@ -290,3 +290,44 @@ def test_solve_reports_failure_when_the_starting_point_cannot_be_evaluated():
         assert gp.evaluate(allow_failure=True)["failed"]
         summ = gp.solve(max_iterations=10)
     assert summ["termination"] == 4 and summ["iterations"] == 0 and summ["accepted"] == 0
+
+
+@pytest.mark.parametrize("shuffled", [False, True])
+def test_integer_pixel_entry_points_are_bit_identical_to_fp64(shuffled):
+    """rcc_ba_set_observations_i16 / _i32 / rcc_ba_update_pixels_i16 (the reference's integer corners,
+    corner_detections.cpp:53-54, camera_pose.cpp:135-142) widen on the device: every result must be bit-identical
+    to the FP64 entry points fed the same integers -- on the golden integer-pixel fixture and on a larger scene,
+    in caller order == sorted order (piecewise overlapped upload) and in a shuffled order."""
+    from helpers import load_golden
+    for s in (load_golden("single_intpix")[0], make_scene(60, 40, 0.7, seed=64, round_pixels=True)):
+        if shuffled:
+            perm = np.random.default_rng(8).permutation(s.n_blocks)
+            s.view_idx, s.marker_idx, s.cam_idx, s.pixels = s.view_idx[perm], s.marker_idx[perm], s.cam_idx[perm], s.pixels[perm]
+        assert np.array_equal(s.pixels, np.trunc(s.pixels))
+        pix2 = np.trunc(s.pixels + np.random.default_rng(9).integers(-2, 3, s.pixels.shape))
+
+        def run(gp):
+            c = gp.linearize()
+            nb = gp.normal_blocks()
+            ev = gp.evaluate(want_jacobians=False)
+            return [c, ev["residuals"]] + [nb[k] for k in ("Hee", "Hff", "W", "ge", "gf", "Hes", "Hfs", "Hss", "gs")]
+
+        with BAProblem.from_scene(s) as gp:
+            ref1 = run(gp)
+            gp.update_pixels(pix2)
+            ref2 = run(gp)
+        for dt in (np.int16, np.int32):
+            si = make_scene(3, 3, 1.0, seed=1)          # container only
+            import copy
+            si = copy.copy(s)
+            si.pixels = s.pixels.astype(dt)
+            with BAProblem.from_scene(si) as gp:
+                got1 = run(gp)
+                gp.update_pixels(pix2.astype(np.int16))
+                got2 = run(gp)
+                gp.update_pixels(s.pixels.astype(np.int16))
+                gp.update_pixels(pix2.astype(np.int16))       # overwritten before anything consumed it
+                got3 = run(gp)
+            for want, got in ((ref1, got1), (ref2, got2), (ref2, got3)):
+                for a, b in zip(want, got):
+                    assert np.array_equal(np.asarray(a), np.asarray(b))

@@ -81,7 +81,8 @@ def test_gpu_pnp_matches_cv2_solvepnp():
     poses, cost = initialiser.pnp_batch(intr, dist, s.sizes[s.marker_idx], s.pixels, max_iterations=100)
     assert (cost >= 0).all()
     K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
-    worst_cv = worst_tight = worst_raw = 0.0
+    worst_cv = worst_tight = 0.0
+    raw = []
     for b in range(0, s.n_blocks, 5):
         size = s.sizes[s.marker_idx[b]]
         h = size / 2
@@ -93,12 +94,14 @@ def test_gpu_pnp_matches_cv2_solvepnp():
                                       criteria=(cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 1000, 1e-16))
         x_cv_tight = np.concatenate([r2.ravel(), t2.ravel()])
         x_tight = _tight_pnp(intr, dist, size, s.pixels[b], x_cv)
-        worst_raw = max(worst_raw, np.abs(poses[b] - x_cv).max())
+        raw.append(np.abs(poses[b] - x_cv).max())
         worst_cv = max(worst_cv, np.abs(poses[b] - x_cv_tight).max())
         worst_tight = max(worst_tight, np.abs(poses[b] - x_tight).max())
-    assert worst_tight < 1e-8, (worst_tight, worst_cv, worst_raw)      # rad and m
-    assert worst_cv < 1e-7, (worst_tight, worst_cv, worst_raw)         # OpenCV's LM stops on a parameter-change norm
-    assert worst_raw < 1e-6, (worst_tight, worst_cv, worst_raw)        # the stock call, OpenCV's default tolerance
+    assert worst_tight < 1e-8, (worst_tight, worst_cv, np.median(raw))      # rad and m
+    assert worst_cv < 1e-7, (worst_tight, worst_cv, np.median(raw))         # OpenCV's LM stops on a parameter-change norm
+    # the stock call stops at OpenCV's default tolerance: typically 1e-9 from the minimiser, but up to 0.2 away on
+    # the odd tag whose depth direction is flat (that is why the comparison above polishes it first)
+    assert np.median(raw) < 1e-6, (worst_tight, worst_cv, np.median(raw), max(raw))
     # sanity against ground truth: 0.3 px noise on a ~15 px tag leaves decimetre depth errors at most
     truth = compose(invert(s.truth["views"][s.view_idx]), s.truth["markers"][s.marker_idx])
     assert np.median(np.abs(poses[:, 3:] - truth[:, 3:])) < 0.02
@@ -112,10 +115,10 @@ def test_initialise_matches_the_cv2_restatement_and_feeds_ba():
     frames = _frames(s)
     intr, dist = s.truth["intr"][0], s.truth["dist"][0]
     scene, ids, kept = initialiser.initialise(frames, intr, dist)
-    o_ids, o_sizes, o_wTt, o_wTc = pnp_oracle.initialise(frames, intr, dist)
+    o_ids, o_sizes, o_wTt, o_wTc = pnp_oracle.initialise(frames, intr, dist, polish=True)
     assert list(ids) == list(o_ids)
     assert list(kept) == [n for n, t in enumerate(o_wTc) if t is not None]
-    # chained poses: products of up to ~10 PnP solutions, each within OpenCV's default stopping tolerance (~1e-8)
+    # chained poses: products of a few PnP solutions, each converged to ~1e-8 on both sides
     assert np.abs(rodrigues_np(scene.markers[:, :3]) - rodrigues_np(o_wTt[:, :3])).max() < 1e-6
     assert np.abs(scene.markers[:, 3:] - o_wTt[:, 3:]).max() < 1e-6
     # the initial guess is good enough for the bundle adjustment to converge

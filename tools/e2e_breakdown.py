@@ -5,7 +5,7 @@ import numpy as np, torch
 from bench import workload
 from robot_camera_calibration_b200.problem import BAProblem, _dp
 
-scene, desc = workload(2, 0, 1.0)
+scene, desc, _ = workload(2, 0, 1, 1.0)
 gp = BAProblem.from_scene(scene, eliminate="views")
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 h_pix, h_views, h_markers = pin(scene.pixels), pin(scene.views.copy()), pin(scene.markers.copy())

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import workload
 from robot_camera_calibration_b200.problem import BAProblem
-s, _ = workload(2, 0, 1.0)
+s, _, _ = workload(2, 0, 1, 1.0)
 gp = BAProblem.from_scene(s)
 for _ in range(3):
     gp.evaluate_device(True)

@@ -10,7 +10,7 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 lm = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-scene, desc = workload(cfg, 0, scale)
+scene, desc, _ = workload(cfg, 0, 1, scale)
 gp = BAProblem.from_scene(scene, eliminate="views")
 for _ in range(3):
     gp.linearize(want_cost=False)

@@ -8,7 +8,7 @@ from robot_camera_calibration_b200.problem import BAProblem
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-scene, desc = workload(cfg, 0, scale)
+scene, desc, _ = workload(cfg, 0, 1, scale)
 gp = BAProblem.from_scene(scene, eliminate="views")
 gp.linearize(want_cost=False)
 for _ in range(2):
