@@ -216,6 +216,13 @@ int64_t rcc_ba_launch_count(const rcc_ba_problem* p);
 int rcc_ba_synchronize(rcc_ba_problem* p);
 /* writes >= bytes to a scratch buffer to evict L2 between timed iterations */
 int rcc_ba_flush_l2(rcc_ba_problem* p);
+/* The dense Cholesky of the reduced solve on its own (tests, timing): factors in place the n x n SPD matrix whose
+ * LOWER triangle is stored column-major with leading dimension ld (even, > n + extra_rows) in DEVICE memory dA;
+ * rows n .. n+extra_rows-1 ride along as bordered right-hand sides (they come back multiplied by L^-T from the
+ * right, i.e. as forward-substituted vectors).  use_cusolver != 0 runs cusolverDnDpotrf instead (the comparator;
+ * extra_rows must be 0).  info: 0 or 1 + the first column with a non-positive pivot; ms: device time. */
+int rcc_dense_potrf(int32_t device, double* dA, int32_t n, int32_t ld, int32_t extra_rows, int32_t use_cusolver,
+                    int32_t* info, double* ms);
 /* FP64 FMA microbenchmark for the roofline denominator: returns TFLOP/s */
 int rcc_fp64_peak_tflops(int32_t device, double* tflops);
 

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librcc_ba.so")
-SOURCES = ["assemble.cu", "evaluate.cu", "schur.cu", "problem.cu", "pnp.cu"]
+SOURCES = ["assemble.cu", "evaluate.cu", "schur.cu", "dense.cu", "problem.cu", "pnp.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-O3", "-Xptxas", "-v",

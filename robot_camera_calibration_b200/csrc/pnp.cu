@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(128) pnp_kernel(int64_t n, const double* __res
     const double c2 = pnp_cost<false>(q, sh, hs, pix, nullptr, nullptr, &ok2);
     // Accept on "not worse up to rounding": along the weakly determined depth direction of a small tag the cost is
     // flat to 1e-16 relative while the step is still 1e-8, so convergence is declared on the step alone.
-    if (ok2 && c2 <= cost * (1.0 + 4e-16)) {
+    // Below a relative step of 1e-5 the Gauss-Newton model is exact to rounding while the cost comparison is pure
+    // noise (it would stall the iteration ~1e-8 short of the minimiser): such steps are taken on trust.
+    const bool tiny = dn <= 1e-10 * (pn + 1e-10);
+    if (ok2 && (tiny || c2 <= cost * (1.0 + 4e-16))) {
       for (int a = 0; a < 6; ++a) p[a] = q[a];
       cost = pnp_cost<true>(p, sh, hs, pix, H, g, &ok);
       lambda = fmax(lambda * 0.1, 1e-12);

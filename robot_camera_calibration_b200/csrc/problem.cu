@@ -85,6 +85,7 @@ struct Scoped {
 }  // namespace rcc
 
 rcc_ba_problem::~rcc_ba_problem() {
+  chol.destroy();
   if (comm) ncclCommDestroy(comm);
   if (solver) cusolverDnDestroy(solver);
   if (blas) cublasDestroy(blas);
@@ -611,6 +612,26 @@ __global__ void extract_rhs_kernel(const double* __restrict__ S, int n, int ld, 
   if (i < n) rhs[i] = -S[(size_t)i * ld + n];
 }
 
+// which factorisation the reduced solve uses (RCC_CHOLESKY overrides; resolved once per handle and communicator)
+static int cholesky_mode(P_t* P) {
+  if (P->chol_mode >= 0) return P->chol_mode;
+  const char* v = getenv("RCC_CHOLESKY");
+  const std::string s = v ? v : "auto";
+  const bool multi = P->comm != nullptr && P->n_ranks > 1;
+  int mode;
+  if (s == "cusolver") mode = 0;
+  else if (s == "own") mode = 1;
+  else if (s == "dist") mode = multi ? 2 : 1;
+  else {
+    // auto: the hand-written factorisation pays off where its trailing update dominates; below that the panel
+    // latency of 128-column steps loses to cuSOLVER (measured)
+    const int n_min = env_int("RCC_CHOL_MIN_N", 6000);
+    mode = P->n_red >= n_min ? (multi ? 2 : 1) : 0;
+  }
+  P->chol_mode = mode;
+  return mode;
+}
+
 // all-reduce + damping/mask + Cholesky + back-substitution + candidate parameters
 static void do_step(P_t* P) {
   RCC_REQUIRE(P->schur_done, RCC_NOT_READY, "schur has not been called");
@@ -633,9 +654,20 @@ static void do_step(P_t* P) {
     // leaves y = L^-1 b in that row -- the forward substitution comes out of potrf for free -- and one
     // triangular solve L^T x = -y remains (cusolverDnDpotrs would run two).
     Scoped t(P, ST_CHOLESKY, 4);
-    set_border_pivot_kernel<<<1, 1, 0, P->stream>>>(P->S.p + (size_t)n * P->ld + n);
-    RCC_SOLVER(cusolverDnDpotrf(P->solver, CUBLAS_FILL_MODE_LOWER, n + 1, P->S.p, P->ld, P->potrf_work.p,
-                                P->potrf_lwork, P->dev_info.p));
+    const int mode = cholesky_mode(P);
+    if (mode == 0) {
+      set_border_pivot_kernel<<<1, 1, 0, P->stream>>>(P->S.p + (size_t)n * P->ld + n);
+      RCC_SOLVER(cusolverDnDpotrf(P->solver, CUBLAS_FILL_MODE_LOWER, n + 1, P->S.p, P->ld, P->potrf_work.p,
+                                  P->potrf_lwork, P->dev_info.p));
+    } else {
+      // dense.cu: the right-hand side is row n of every panel (never a column), so no border pivot is needed.
+      // mode 2: block column J is factored and updated by rank J % n_ranks, finished panels are broadcast in place.
+      const int64_t before = P->chol.launches;
+      chol_factor(P->S.p, n, P->ld, n + 1, P->rank, mode == 2 ? P->n_ranks : 1, mode == 2 ? P->comm : nullptr,
+                  P->stream, P->chol);
+      P->launch_count += P->chol.launches - before;
+      RCC_CUDA(cudaMemcpyAsync(P->dev_info.p, P->chol.info, sizeof(int), cudaMemcpyDeviceToDevice, P->stream));
+    }
     extract_rhs_kernel<<<ceil_div(n, 256), 256, 0, P->stream>>>(P->S.p, n, P->ld, P->rhs.p);
     RCC_CUDA(cudaGetLastError());
     RCC_BLAS(cublasDtrsv(P->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n, P->S.p, P->ld,
@@ -1471,6 +1503,7 @@ int rcc_ba_comm_init(rcc_ba_problem* P, const char id[RCC_COMM_ID_BYTES], int32_
   }
   P->rank = rank;
   P->n_ranks = n_ranks;
+  P->chol_mode = -1;   // re-resolve: the distributed factorisation needs the communicator
   if (n_ranks > 1) {
     ncclUniqueId u;
     memcpy(&u, id, sizeof(u));
@@ -1522,6 +1555,58 @@ int rcc_ba_synchronize(rcc_ba_problem* P) {
   API_BEGIN(P)
   sync(P);
   API_END(P)
+}
+
+int rcc_dense_potrf(int32_t device, double* dA, int32_t n, int32_t ld, int32_t extra_rows, int32_t use_cusolver,
+                    int32_t* info, double* ms) {
+  if (!dA || n <= 0 || ld < n + extra_rows || extra_rows < 0) return RCC_BAD_ARG;
+  CholDriver d;
+  cusolverDnHandle_t h = nullptr;
+  double* work = nullptr;
+  int* dinfo = nullptr;
+  cudaStream_t s = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int rc = RCC_OK;
+  try {
+    RCC_CUDA(cudaSetDevice(device));
+    RCC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    RCC_CUDA(cudaEventCreate(&a));
+    RCC_CUDA(cudaEventCreate(&b));
+    int lwork = 0;
+    if (use_cusolver) {
+      RCC_REQUIRE(extra_rows == 0, RCC_BAD_ARG, "the cuSOLVER comparator factors a square matrix");
+      RCC_SOLVER(cusolverDnCreate(&h));
+      RCC_SOLVER(cusolverDnSetStream(h, s));
+      RCC_SOLVER(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, n, dA, ld, &lwork));
+      RCC_CUDA(cudaMalloc(&work, (size_t)std::max(1, lwork) * sizeof(double)));
+      RCC_CUDA(cudaMalloc(&dinfo, sizeof(int)));
+    } else {
+      d.init();
+    }
+    RCC_CUDA(cudaEventRecord(a, s));
+    if (use_cusolver) RCC_SOLVER(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, n, dA, ld, work, lwork, dinfo));
+    else chol_factor(dA, n, ld, n + extra_rows, 0, 1, nullptr, s, d);
+    RCC_CUDA(cudaEventRecord(b, s));
+    RCC_CUDA(cudaStreamSynchronize(s));
+    float t = 0.f;
+    RCC_CUDA(cudaEventElapsedTime(&t, a, b));
+    if (ms) *ms = t;
+    int hinfo = 0;
+    RCC_CUDA(cudaMemcpy(&hinfo, use_cusolver ? dinfo : d.info, sizeof(int), cudaMemcpyDeviceToHost));
+    if (info) *info = hinfo;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    fprintf(stderr, "[rcc_dense_potrf] %s\n", e.what());
+    rc = e.status;
+  }
+  d.destroy();
+  if (h) cusolverDnDestroy(h);
+  if (work) cudaFree(work);
+  if (dinfo) cudaFree(dinfo);
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
+  if (s) cudaStreamDestroy(s);
+  return rc;
 }
 
 int rcc_fp64_peak_tflops(int32_t device, double* tflops) {

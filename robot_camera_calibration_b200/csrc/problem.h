@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dense.h"
 #include "kernels.h"
 
 namespace rcc {
@@ -95,6 +96,11 @@ struct rcc_ba_problem {
   rcc::DBuf<double> potrf_work;
   rcc::DBuf<int> dev_info;
   int potrf_lwork = 0;
+
+  // reduced solve: 0 = cusolverDnDpotrf replicated on every rank, 1 = dense.cu on this rank, 2 = dense.cu with the
+  // block columns distributed over the ranks (RCC_CHOLESKY = cusolver | own | dist | auto)
+  int chol_mode = -1;                    // -1: not resolved yet
+  rcc::CholDriver chol;
 
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
