@@ -20,7 +20,7 @@ for n in sizes:
             buf[:n, :n] = S
             ms = C.c_double()
             rc = lib.rcc_dense_potrf(0, C.c_void_p(buf.data_ptr()), n, ld, 0 if cus else 1, cus, C.byref(info), C.byref(ms))
-            assert rc == 0 and info.value == 0, (rc, info.value)
+            assert rc == 0 and info.value == 0, (name, n, rc, info.value, rep)
             best = min(best, ms.value)
             if rep == 0:
                 Lf = torch.triu(buf[:n, :n]).T
