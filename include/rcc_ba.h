@@ -76,6 +76,9 @@ typedef struct {
   double min_diagonal;            /* 1e-6 */
   double max_diagonal;            /* 1e32 */
   int32_t verbose;
+  int32_t jacobi_scaling;         /* 1 (Ceres default): the LM diagonal is formed on the Jacobian with columns scaled by
+                                   * 1 / (1 + ||column||), i.e. min/max_diagonal clamp s^2 diag(J^T J) instead of
+                                   * diag(J^T J); the step is returned in unscaled parameters */
 } rcc_lm_options;
 
 typedef struct {
@@ -159,8 +162,10 @@ int rcc_ba_evaluate_device(rcc_ba_problem* p, int32_t want_jacobians, double* co
 /* ---- normal equations, Schur complement, LM step ------------------------- */
 /* residual + Jacobian + J^T J / J^T r blocks, fused (no Jacobian in HBM) */
 int rcc_ba_linearize(rcc_ba_problem* p, double* cost /*may be NULL: no host sync*/);
-/* damped Schur complement into the reduced system (local partial on this rank) */
+/* damped Schur complement into the reduced system (local partial on this rank).  Uses the LM diagonal bounds and
+ * the Jacobi-scaling flag of the last rcc_ba_solve / rcc_ba_set_lm_diagonal (defaults 1e-6, 1e32, no scaling). */
 int rcc_ba_schur(rcc_ba_problem* p, double radius);
+int rcc_ba_set_lm_diagonal(rcc_ba_problem* p, double min_diagonal, double max_diagonal, int32_t jacobi_scaling);
 /* [all-reduce over ranks] + constant mask + Cholesky + back-substitution.
  * model_cost_change may be NULL. */
 int rcc_ba_solve_step(rcc_ba_problem* p, double* model_cost_change, double* step_norm, double* x_norm);

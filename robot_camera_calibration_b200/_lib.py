@@ -35,7 +35,8 @@ class LMOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("initial_radius", C.c_double), ("max_radius", C.c_double),
                 ("min_relative_decrease", C.c_double), ("function_tolerance", C.c_double),
                 ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
-                ("min_diagonal", C.c_double), ("max_diagonal", C.c_double), ("verbose", C.c_int32)]
+                ("min_diagonal", C.c_double), ("max_diagonal", C.c_double), ("verbose", C.c_int32),
+                ("jacobi_scaling", C.c_int32)]
 
 
 class LMSummary(C.Structure):
@@ -81,6 +82,7 @@ SIGNATURES = {
     "rcc_ba_evaluate_device": (C.c_int, [_H, C.c_int32, c_double_p]),
     "rcc_ba_linearize": (C.c_int, [_H, c_double_p]),
     "rcc_ba_schur": (C.c_int, [_H, C.c_double]),
+    "rcc_ba_set_lm_diagonal": (C.c_int, [_H, C.c_double, C.c_double, C.c_int32]),
     "rcc_ba_solve_step": (C.c_int, [_H, c_double_p, c_double_p, c_double_p]),
     "rcc_ba_candidate_cost": (C.c_int, [_H, c_double_p]),
     "rcc_ba_accept_step": (C.c_int, [_H]),

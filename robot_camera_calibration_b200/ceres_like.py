@@ -80,7 +80,7 @@ class SolverOptions:
     def __init__(self, max_num_iterations=50, initial_trust_region_radius=1e4, max_trust_region_radius=1e16,
                  min_relative_decrease=1e-3, function_tolerance=1e-6, gradient_tolerance=1e-10,
                  parameter_tolerance=1e-8, min_lm_diagonal=1e-6, max_lm_diagonal=1e32,
-                 minimizer_progress_to_stdout=False):
+                 minimizer_progress_to_stdout=False, jacobi_scaling=True):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -225,7 +225,8 @@ def Solve(options, problem):
                      max_radius=o.max_trust_region_radius, min_relative_decrease=o.min_relative_decrease,
                      function_tolerance=o.function_tolerance, gradient_tolerance=o.gradient_tolerance,
                      parameter_tolerance=o.parameter_tolerance, min_diagonal=o.min_lm_diagonal,
-                     max_diagonal=o.max_lm_diagonal, verbose=int(o.minimizer_progress_to_stdout))
+                     max_diagonal=o.max_lm_diagonal, verbose=int(o.minimizer_progress_to_stdout),
+                     jacobi_scaling=int(o.jacobi_scaling))
         views, markers = gp.get_view_poses(), gp.get_marker_poses()
         intr, dist = gp.get_intrinsics()
         ext = gp.get_rig_extrinsics() if rig else None

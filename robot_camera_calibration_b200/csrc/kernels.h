@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace rcc {
@@ -152,6 +153,15 @@ void launch_sum(const double* in, int64_t n, double* out, double scale, cudaStre
 // ---------------------------------------------------------------------------
 // K3: Schur complement
 // ---------------------------------------------------------------------------
+// LM damping of one parameter from its diag(J^T J) entry h (Ceres: D^2 = clamp(diag) / radius).  With Jacobi
+// scaling the clamp applies to the scaled column, s = 1 / (1 + sqrt(h)), and the result is mapped back to the
+// unscaled parameter:  clamp(s^2 h) / (radius s^2).
+__host__ __device__ inline double lm_diagonal(double h, double radius, double min_diag, double max_diag, int jacobi) {
+  if (!jacobi) return fmin(fmax(h, min_diag), max_diag) / radius;
+  const double s = 1.0 / (1.0 + sqrt(fmax(h, 0.0)));
+  return fmin(fmax(h * s * s, min_diag), max_diag) / (radius * s * s);
+}
+
 struct SchurPrepArgs {
   int32_t n_e;
   int32_t n_shared;
@@ -167,6 +177,7 @@ struct SchurPrepArgs {
                                  // consecutive positions (then W of pair p0+i is W[row_pos0 + i]); -1 otherwise
   const double* W;               // [n_obs*36]
   double radius, min_diag, max_diag;
+  int32_t jacobi;                // LM diagonal on the Jacobi-scaled columns (lm_diagonal())
   double* Linv;                  // [n_e*36] row-major lower-triangular inverse of chol(Hee + D)
   double* Y;                     // [n_pairs*36] column-major 6x6 blocks  L^-1 W
   double* Yb;                    // [n_e*n_bb*36] column-major blocks L^-1 [Hes | ge | 0]
@@ -225,6 +236,7 @@ void launch_reduced_tail(const ReducedTailArgs& a, cudaStream_t s);
 struct MaskArgs {
   int32_t n, ld;
   double radius, min_diag, max_diag;
+  int32_t jacobi;
   const int32_t* const_idx;  // reduced-system indices held constant
   int32_t n_const;
   double* S;                 // damping added to the diagonal, constants masked

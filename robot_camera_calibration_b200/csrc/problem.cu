@@ -541,7 +541,7 @@ static void do_schur(P_t* P, double radius) {
     a.n_e = P->n_e; a.n_shared = P->n_shared; a.n_bb = P->n_bb;
     a.Hee = P->Hee.p; a.ge = P->ge.p; a.Hes = P->Hes.p; a.e_const = P->e_const.p;
     a.row_ptr = P->row_ptr.p; a.pair_mptr = P->pair_mptr.p; a.pair_members = P->pair_members.p; a.row_pos0 = P->row_pos0.p; a.W = P->W.p;
-    a.radius = radius; a.min_diag = P->min_diag; a.max_diag = P->max_diag;
+    a.radius = radius; a.min_diag = P->min_diag; a.max_diag = P->max_diag; a.jacobi = P->jacobi;
     a.Linv = P->Linv.p; a.Y = P->Y.p; a.Yb = P->Yb.p; a.d2e = P->d2e.p;
     launch_schur_prep(a, P->stream);
   }
@@ -643,7 +643,7 @@ static void do_step(P_t* P) {
   }
   {
     Scoped t(P, ST_MASK, 3);
-    MaskArgs m{n, P->ld, P->radius_used, P->min_diag, P->max_diag, P->const_idx.p, P->n_const, P->S.p, P->rhs.p,
+    MaskArgs m{n, P->ld, P->radius_used, P->min_diag, P->max_diag, P->jacobi, P->const_idx.p, P->n_const, P->S.p, P->rhs.p,
                P->d2f.p, P->gFm.p};
     launch_mask_damp(m, P->stream);
     copy_scalar_kernel<<<1, 1, 0, P->stream>>>(P->S.p + (size_t)n * P->ld + 2 * n, P->stats.p + SX_COST2);
@@ -791,6 +791,7 @@ static void do_solve(P_t* P, const rcc_lm_options& o, rcc_lm_summary& sum) {
   memset(&sum, 0, sizeof(sum));
   P->min_diag = o.min_diagonal;
   P->max_diag = o.max_diagonal;
+  P->jacobi = o.jacobi_scaling ? 1 : 0;
   double radius = o.initial_radius, decrease = 2.0;
   bool need_lin = true;
   const bool was_on = P->timer.on;
@@ -923,6 +924,7 @@ void rcc_lm_default_options(rcc_lm_options* o) {
   o->min_diagonal = 1e-6;
   o->max_diagonal = 1e32;
   o->verbose = 0;
+  o->jacobi_scaling = 1;
 }
 
 int rcc_ba_create(const rcc_ba_options* opt, rcc_ba_problem** out) {
@@ -1338,6 +1340,16 @@ int rcc_ba_linearize(rcc_ba_problem* P, double* cost) {
 int rcc_ba_schur(rcc_ba_problem* P, double radius) {
   API_BEGIN(P)
   do_schur(P, radius);
+  API_END(P)
+}
+
+int rcc_ba_set_lm_diagonal(rcc_ba_problem* P, double min_diagonal, double max_diagonal, int32_t jacobi_scaling) {
+  API_BEGIN(P)
+  RCC_REQUIRE(min_diagonal >= 0 && max_diagonal >= min_diagonal, RCC_BAD_ARG, "bad LM diagonal bounds");
+  P->min_diag = min_diagonal;
+  P->max_diag = max_diagonal;
+  P->jacobi = jacobi_scaling ? 1 : 0;
+  P->schur_done = P->step_ready = P->cand_ready = false;
   API_END(P)
 }
 

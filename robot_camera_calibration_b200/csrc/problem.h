@@ -107,6 +107,7 @@ struct rcc_ba_problem {
 
   bool have_obs = false, linearized = false, schur_done = false, step_ready = false, cand_ready = false;
   double min_diag = 1e-6, max_diag = 1e32;
+  int jacobi = 0;                    // Jacobi column scaling of the LM diagonal
   int loss = 0;
   double loss_scale = 1.0;
   rcc::StageTimer timer;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128, 3) schur_prep_kernel(const SchurPrepArgs 
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const double dg = H[i * 6 + i];
-    d2[i] = fmin(fmax(dg, a.min_diag), a.max_diag) / a.radius;
+    d2[i] = lm_diagonal(dg, a.radius, a.min_diag, a.max_diag, a.jacobi);
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
@@ -576,7 +576,7 @@ __global__ void damp_kernel(const MaskArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const double* tail = a.S + (size_t)a.n * a.ld;
-  const double d2 = fmin(fmax(tail[i], a.min_diag), a.max_diag) / a.radius;
+  const double d2 = lm_diagonal(tail[i], a.radius, a.min_diag, a.max_diag, a.jacobi);
   a.S[(size_t)i * a.ld + i] += d2;
   a.d2f[i] = d2;
   a.rhs[i] = -a.S[(size_t)i * a.ld + a.n];

@@ -219,6 +219,9 @@ class BAProblem:
                                                                 ("Hee", "ge", "Hes", "Hff", "gf", "Hfs", "Hss", "gs", "W")]))
         return out
 
+    def set_lm_diagonal(self, min_diagonal=1e-6, max_diagonal=1e32, jacobi_scaling=False):
+        self._check(self.lib.rcc_ba_set_lm_diagonal(self.h, float(min_diagonal), float(max_diagonal), int(jacobi_scaling)))
+
     def schur(self, radius):
         self._check(self.lib.rcc_ba_schur(self.h, float(radius)))
 

@@ -254,3 +254,48 @@ def test_converged_parameters_match_an_independent_solver():
     assert np.abs(markers - ref.markers).max() < 1e-6
     assert np.abs(dist - ref.dist).max() < 1e-6
     assert np.abs(intr - ref.intr).max() < 1e-4      # pixels
+
+
+def test_jacobi_scaling_changes_only_the_clamped_diagonal():
+    """rcc_lm_options.jacobi_scaling (Ceres's default): the LM diagonal clamp(s^2 diag J^T J) / (radius s^2),
+    s = 1 / (1 + ||column||), equals diag(J^T J) / radius wherever the clamp is inactive, so the damped step and the
+    minimiser must not move; where min_diagonal does bite (a parameter the data barely constrain) the scaled
+    diagonal is the one the oracle formula gives."""
+    s = make_scene(12, 30, 0.7, seed=33)
+    p = to_oracle(s)
+    H, g, _ = O.normal_equations(p)
+    steps = {}
+    for jac in (False, True):
+        with BAProblem.from_scene(s, eliminate="views") as gp:
+            gp.set_lm_diagonal(1e-6, 1e32, jac)
+            gp.linearize(); gp.schur(1e3); gp.solve_step()
+            st = gp.step()
+            steps[jac] = np.concatenate([st["d_e"].ravel(), st["d_f"].ravel(), st["d_shared"]])
+    hd = np.diag(H)
+    sc = 1.0 / (1.0 + np.sqrt(hd))
+    assert (hd * sc * sc).min() > 1e-6                      # no clamp on this scene: identical damping
+    assert rel_fro(steps[True], steps[False]) < 1e-9
+    # converged parameters with and without scaling (Ceres-like defaults on both sides)
+    out = {}
+    for jac in (0, 1):
+        with BAProblem.from_scene(s) as gp:
+            summ = gp.solve(max_iterations=40, function_tolerance=1e-14, gradient_tolerance=1e-12,
+                            parameter_tolerance=1e-13, jacobi_scaling=jac)
+            out[jac] = (gp.get_view_poses(), gp.get_marker_poses(), gp.get_intrinsics(), summ)
+    assert np.abs(out[0][0] - out[1][0]).max() < 1e-8 and np.abs(out[0][1] - out[1][1]).max() < 1e-8
+    assert abs(out[0][3]["final_cost"] - out[1][3]["final_cost"]) <= 1e-12 * out[0][3]["final_cost"]
+    # a clamp that bites: min_diagonal = 10 exceeds s^2 h (< 1) everywhere, so with scaling every parameter is damped
+    # by 10 / (radius s^2) = 10 (1 + sqrt(h))^2 / radius; the oracle's dense solve with that diagonal must agree
+    radius = 1e3
+    with BAProblem.from_scene(s, eliminate="views") as gp:
+        gp.set_lm_diagonal(10.0, 1e32, True)
+        gp.linearize(); gp.schur(radius); gp.solve_step()
+        st = gp.step()
+    cm = p.const_mask()
+    d2 = 10.0 * (1.0 + np.sqrt(hd)) ** 2 / radius
+    Hd, gm = O.masked_system(H + np.diag(d2), g, cm)
+    want = -np.linalg.solve(Hd, gm)
+    want[cm] = 0
+    o_view, o_marker, o_shared, n = p.offsets()
+    got = np.concatenate([st["d_e"].ravel(), st["d_f"].ravel(), st["d_shared"]])
+    assert rel_fro(got, want) < 1e-7
