@@ -89,8 +89,8 @@ __device__ int warp_potrf32(double* blk, int st, double* inv, int lane) {
       if (!bad) bad = j + 1;
       d = 1.0;
     }
-    const double r = 1.0 / sqrt(d);
-    const double lj = a[j] * r;    // L(i, j) for lanes i >= j (lane j: sqrt(d))
+    const double r = rsqrt(d);
+    const double lj = a[j] * r;    // L(i, j) for lanes i >= j (lane j: sqrt(d) = d / sqrt(d))
     a[j] = lj;
     if (lane == j) rdiag = r;
 #pragma unroll
@@ -107,10 +107,16 @@ __device__ int warp_potrf32(double* blk, int st, double* inv, int lane) {
   double m[SB];
 #pragma unroll
   for (int i = 0; i < SB; ++i) {
-    double s = (i == lane) ? 1.0 : 0.0;
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;    // four chains: FMA latency, not 4x the work
 #pragma unroll
-    for (int p = 0; p < i; ++p) s = fma(-blk[p * st + i], m[p], s);      // uniform address: broadcast
-    m[i] = s * __shfl_sync(0xffffffffu, rdiag, i);
+    for (int p = 0; p < i; ++p) {                                        // blk[..]: uniform address = broadcast
+      const double l = blk[p * st + i];
+      if ((p & 3) == 0) s0 = fma(-l, m[p], s0);
+      else if ((p & 3) == 1) s1 = fma(-l, m[p], s1);
+      else if ((p & 3) == 2) s2 = fma(-l, m[p], s2);
+      else s3 = fma(-l, m[p], s3);
+    }
+    m[i] = ((s0 + s1) + (s2 + s3)) * __shfl_sync(0xffffffffu, rdiag, i);
   }
 #pragma unroll
   for (int i = 0; i < SB; ++i) inv[lane * IST + i] = m[i];               // inv(n = i, k = lane)
@@ -128,17 +134,22 @@ __global__ void __launch_bounds__(128, 1) chol_diag_kernel(double* __restrict__ 
   double* Ls = sm;                       // [NB][LST] column-major
   double* Is = sm + NB * LST;            // [SB][IST] inverse of the current diagonal sub-block
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // load the lower triangle; rows/columns >= kb are padded with the identity
-  for (int idx = tid; idx < NB * NB; idx += 128) {
-    const int j = idx >> 7, i = idx & (NB - 1);
-    double v = 0.0;
-    if (i >= j) {
-      if (i < kb) v = A[(size_t)(k0 + j) * ld + k0 + i];
-      else if (i == j) v = 1.0;
-    }
-    Ls[j * LST + i] = v;
+  // load the block (asynchronous 16-byte copies, all in flight at once: a plain load loop would pay the memory
+  // latency 128 times); the strict upper triangle comes along and is never used; rows/columns >= kb are padded
+  // with the identity
+  for (int idx = tid; idx < NB * (NB / 2); idx += 128) {
+    const int j = idx >> 6, i2 = (idx & 63) * 2;
+    const bool ok = j < kb && i2 + 1 >= j && i2 < kb;
+    cp_async16(Ls + j * LST + i2, ok ? A + (size_t)(k0 + j) * ld + k0 + i2 : A, ok ? 16 : 0);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
+  if (kb < NB) {
+    if (tid >= kb) Ls[tid * LST + tid] = 1.0;
+    if ((kb & 1) && tid < kb) Ls[tid * LST + kb] = 0.0;      // the pair (kb-1, kb) brought one row too many
+    __syncthreads();
+  }
   for (int c = 0; c < NB / SB; ++c) {
     const int c0 = c * SB;
     // (1) left-looking: rows >= c0 of block column c  -=  L(rows, 0:c0) L(c0:c0+32, 0:c0)^T ; warp w takes the
@@ -212,15 +223,16 @@ __global__ void __launch_bounds__(128, 1) chol_panel_kernel(double* __restrict__
     cp_async16(Xs + c * XST + r2, ok ? A + (size_t)(k0 + c) * ld + i0 + r2 : A, ok ? 16 : 0);
   }
   cp_async_commit();
-  for (int idx = tid; idx < 6 * SB * SB; idx += 128) {
-    const int blk = idx >> 10, k = (idx >> 5) & 31, n = idx & 31;
+  for (int idx = tid; idx < 6 * SB * (SB / 2); idx += 128) {
+    const int blk = idx >> 9, k = (idx >> 4) & 31, n = (idx & 15) * 2;
     const int c = blk < 1 ? 1 : (blk < 3 ? 2 : 3), p = blk - (c * (c - 1)) / 2;
-    Lb[blk * SB * IST + k * IST + n] = Lw[(SB * p + k) * NB + SB * c + n];
+    cp_async16(Lb + blk * SB * IST + k * IST + n, Lw + (SB * p + k) * NB + SB * c + n, 16);
   }
-  for (int idx = tid; idx < 4 * SB * SB; idx += 128) {
-    const int c = idx >> 10, k = (idx >> 5) & 31, n = idx & 31;
-    Ib[c * SB * IST + k * IST + n] = inv32[idx];
+  for (int idx = tid; idx < 4 * SB * (SB / 2); idx += 128) {
+    const int c = idx >> 9, k = (idx >> 4) & 31, n = (idx & 15) * 2;
+    cp_async16(Ib + c * SB * IST + k * IST + n, inv32 + c * SB * SB + k * SB + n, 16);
   }
+  cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
   // warp w owns rows 16w .. 16w+15 of the strip through all four sub-steps
@@ -345,10 +357,16 @@ __global__ void __launch_bounds__(128, 2) chol_update_kernel(const UpdateArgs a)
       const int col = jb + 8 * j + q;
       if (col >= a.n_cols) continue;
       double* cp = a.A + (size_t)col * a.ld;
+      double cv[8];          // all 8 loads of the column in flight before the first store (read-modify-write latency once)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = ib + 8 * i;
-        if (row >= col && row < a.n_rows) cp[row] -= acc[i][j][q];
+        cv[i] = (row >= col && row < a.n_rows) ? cp[row] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = ib + 8 * i;
+        if (row >= col && row < a.n_rows) cp[row] = cv[i] - acc[i][j][q];
       }
     }
 }

@@ -8,6 +8,7 @@
 #include "problem.h"
 #include "model.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges are no-ops unless a profiler is attached
 #include <omp.h>
 #include <string.h>
 
@@ -73,13 +74,19 @@ StageTimer::~StageTimer() {
   for (auto e : pool) cudaEventDestroy(e);
 }
 
+// one pipeline stage: CUDA-event timing (rcc_ba_profile_*), launch accounting and an NVTX range named after the
+// stage (K0 expand ... K6 cost), so that a timeline tool shows the same stages the profile API reports
 struct Scoped {
   rcc_ba_problem* P;
   Scoped(rcc_ba_problem* p, int stage, int n_launch) : P(p) {
+    nvtxRangePushA(stage_name(stage));
     P->timer.begin(stage, P->stream);
     P->launch_count += n_launch;
   }
-  ~Scoped() { P->timer.end(P->stream); }
+  ~Scoped() {
+    P->timer.end(P->stream);
+    nvtxRangePop();
+  }
 };
 
 }  // namespace rcc

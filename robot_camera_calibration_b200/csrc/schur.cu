@@ -209,6 +209,9 @@ constexpr int SY_G = SY_SUB / 32;    // tile_ptr entries per warp sub-tile
 #ifndef RCC_SY_BATCH
 #define RCC_SY_BATCH 32
 #endif
+#ifndef RCC_SY_PF
+#define RCC_SY_PF 1      // prefetch depth of the partner-column loads, in 32-item steps
+#endif
 constexpr int SY_BATCH = RCC_SY_BATCH;   // pairs of column f staged per round (<= 32: one lane per pair holds its range)
 static_assert(SY_BATCH <= 32, "a batch must fit the lanes of a warp");
 static_assert(SY_SUB % 32 == 0, "warp sub-tile must be a multiple of the tile_ptr granularity");
@@ -309,12 +312,26 @@ __global__ void __launch_bounds__(SY_WARPS * 32, RCC_SY_CTAS) schur_syrk_kernel(
       SyItem it_c, it_n;
       bool have = sy_advance(cur, nb, lo_cur, hi_cur);
       if (have) sy_load(a, cur, lane, subbase, it_c);
+#if RCC_SY_PF >= 2
+      // second prefetch stage: the partner columns come from L2 (~600 cycles) and one step lasts ~200
+      SyCursor nn2;
+      SyItem it_nn;
+      nxt = cur;
+      bool have_n = have && sy_advance(nxt, nb, lo_cur, hi_cur);
+      if (have_n) sy_load(a, nxt, lane, subbase, it_n);
+#endif
       int q_loaded = -1;
       double Yi[36];   // Y_ef, column-major: Yi[r * 6 + k] = Y_ef[k][r]
       while (have) {
+#if RCC_SY_PF >= 2
+        nn2 = nxt;
+        const bool have_nn = have_n && sy_advance(nn2, nb, lo_cur, hi_cur);
+        if (have_nn) sy_load(a, nn2, lane, subbase, it_nn);
+#else
         nxt = cur;
         const bool have_n = sy_advance(nxt, nb, lo_cur, hi_cur);
         if (have_n) sy_load(a, nxt, lane, subbase, it_n);
+#endif
         if (cur.q != q_loaded) {
           const double2* src = reinterpret_cast<const double2*>(ybuf + cur.q * 36);
 #pragma unroll
@@ -348,6 +365,11 @@ __global__ void __launch_bounds__(SY_WARPS * 32, RCC_SY_CTAS) schur_syrk_kernel(
         cur = nxt;
         it_c = it_n;
         have = have_n;
+#if RCC_SY_PF >= 2
+        nxt = nn2;
+        it_n = it_nn;
+        have_n = have_nn;
+#endif
       }
     }
     lo_cur = lo_nxt;

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 name=$1; defs=$2
 pkg=robot_camera_calibration_b200
 out=$pkg/build/variants; mkdir -p $out/$name
-for f in assemble evaluate schur problem pnp; do
+for f in assemble evaluate schur dense problem pnp; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fopenmp,-O3 \
     --expt-relaxed-constexpr $defs -c $pkg/csrc/$f.cu -o $out/$name/$f.o &
 done
