@@ -252,10 +252,17 @@ def multi_gpu_parity(torch, dist, rank, world, local):
     from robot_camera_calibration_b200.scenes import make_scene
     out = {}
     rel = lambda a, b: float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300))
-    cases = (("single", dict(n_markers=60, n_views=max(96, 12 * world), visibility=0.5, seed=77)),
-             ("rig", dict(n_markers=40, n_views=max(64, 8 * world), visibility=0.5, n_cam=2, model="rig", seed=78)))
-    for name, kw in cases:
+    # "dist": the hand-written Cholesky with its block columns distributed over the ranks and the panels broadcast
+    # (what cfg4 uses; forced here because these scenes are far below the size where it is chosen automatically);
+    # "replicated": every rank factors the all-reduced system itself
+    cases = (("single_dist", "dist", dict(n_markers=60, n_views=max(96, 12 * world), visibility=0.5, seed=77)),
+             ("single_replicated", "cusolver", dict(n_markers=60, n_views=max(96, 12 * world), visibility=0.5, seed=77)),
+             ("rig_dist", "dist", dict(n_markers=40, n_views=max(64, 8 * world), visibility=0.5, n_cam=2, model="rig",
+                                       seed=78)))
+    saved = os.environ.get("RCC_CHOLESKY")
+    for name, chol, kw in cases:
         kw = dict(kw)
+        os.environ["RCC_CHOLESKY"] = chol
         scene = make_scene(kw.pop("n_markers"), kw.pop("n_views"), kw.pop("visibility"), **kw)
         local_scene, (lo, hi) = shard_scene(scene, rank, world, "views")
         gp = BAProblem.from_scene(local_scene, device=local, eliminate="views")
@@ -280,6 +287,7 @@ def multi_gpu_parity(torch, dist, rank, world, local):
         dist.all_gather_object(vparts, (lo, hi, views_n[lo:hi]))
         gp.close()
         if rank == 0:
+            os.environ["RCC_CHOLESKY"] = "cusolver"      # the 1-rank comparator factors with the library routine
             with BAProblem.from_scene(scene, device=local, eliminate="views") as g1:
                 g1.linearize()
                 g1.schur(1e4)
@@ -302,6 +310,10 @@ def multi_gpu_parity(torch, dist, rank, world, local):
                          "converged_views_max_abs": float(np.abs(views_all - v1).max()),
                          "converged_markers_max_abs": float(np.abs(markers_n - m1).max())}
         dist.barrier()
+    if saved is None:
+        os.environ.pop("RCC_CHOLESKY", None)
+    else:
+        os.environ["RCC_CHOLESKY"] = saved
     if rank == 0:
         out["tolerance"] = 1e-9
         out["ok"] = bool(all(v["S"] < 1e-9 and v["b"] < 1e-9 and v["delta_F"] < 1e-9 and v["delta_E"] < 1e-9 and

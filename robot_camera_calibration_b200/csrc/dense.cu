@@ -334,41 +334,57 @@ __global__ void __launch_bounds__(128, 2) chol_update_kernel(const UpdateArgs a)
     cp_async_commit();
     const double* as = sm + (kc % UP_STAGES) * UP_STAGE_DOUBLES + wm * 64;
     const double* bs = sm + (kc % UP_STAGES) * UP_STAGE_DOUBLES + UP_BK * UP_AST + wn * 32;
+    // fragments of k-step s+1 are loaded while the 32 MMAs of k-step s issue
+    double af[2][8], bf[2][4];
 #pragma unroll
-    for (int k = 0; k < UP_BK; k += 4) {
-      double af[8], bf[4];
+    for (int i = 0; i < 8; ++i) af[0][i] = as[lk * UP_AST + 8 * i + lr];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) af[i] = as[(k + lk) * UP_AST + 8 * i + lr];
+    for (int j = 0; j < 4; ++j) bf[0][j] = bs[lk * UP_BST + 8 * j + lr];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = bs[(k + lk) * UP_BST + 8 * j + lr];
+    for (int ks = 0; ks < UP_BK / 4; ++ks) {
+      const int cur = ks & 1, nxt = cur ^ 1;
+      if (ks + 1 < UP_BK / 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) af[nxt][i] = as[(4 * (ks + 1) + lk) * UP_AST + 8 * i + lr];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[nxt][j] = bs[(4 * (ks + 1) + lk) * UP_BST + 8 * j + lr];
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(acc[i][j], af[i], bf[j]);
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j], af[cur][i], bf[cur][j]);
     }
   }
   cp_async_wait<0>();
-  // C(i, j) -= acc, lower triangle only
+  // C(i, j) -= acc, lower triangle only.  The tile comes from HBM (~0.8 us): 32 loads are put in flight before the
+  // first store, so the read-modify-write latency is paid twice per tile instead of once per column.
   const int ib = i0 + wm * 64 + lr, jb = j0 + wn * 32 + 2 * lk;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int h = 0; h < 2; ++h) {
+    double cv[4][8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int c = 0; c < 4; ++c) {
+      const int j = 2 * h + (c >> 1), q = c & 1;
       const int col = jb + 8 * j + q;
-      if (col >= a.n_cols) continue;
-      double* cp = a.A + (size_t)col * a.ld;
-      double cv[8];          // all 8 loads of the column in flight before the first store (read-modify-write latency once)
+      const double* cp = a.A + (size_t)col * a.ld;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = ib + 8 * i;
-        cv[i] = (row >= col && row < a.n_rows) ? cp[row] : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = ib + 8 * i;
-        if (row >= col && row < a.n_rows) cp[row] = cv[i] - acc[i][j][q];
+        cv[c][i] = (col < a.n_cols && row >= col && row < a.n_rows) ? cp[row] : 0.0;
       }
     }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = 2 * h + (c >> 1), q = c & 1;
+      const int col = jb + 8 * j + q;
+      double* cp = a.A + (size_t)col * a.ld;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = ib + 8 * i;
+        if (col < a.n_cols && row >= col && row < a.n_rows) cp[row] = cv[c][i] - acc[i][j][q];
+      }
+    }
+  }
 }
 
 SmemOptIn g_diag_optin, g_panel_optin, g_update_optin;

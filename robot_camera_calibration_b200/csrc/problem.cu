@@ -1588,6 +1588,7 @@ int rcc_dense_potrf(int32_t device, double* dA, int32_t n, int32_t ld, int32_t e
   int rc = RCC_OK;
   try {
     RCC_CUDA(cudaSetDevice(device));
+    RCC_CUDA(cudaDeviceSynchronize());      // the caller filled dA on a stream of its own
     RCC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     RCC_CUDA(cudaEventCreate(&a));
     RCC_CUDA(cudaEventCreate(&b));

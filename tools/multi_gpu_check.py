@@ -14,8 +14,16 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 out = {}
 for name, kw in (("single", dict(n_markers=40, n_views=120, visibility=0.5, seed=41)),
-                 ("rig", dict(n_markers=30, n_views=60, visibility=0.5, n_cam=2, model="rig", seed=42))):
+                 ("rig", dict(n_markers=30, n_views=60, visibility=0.5, n_cam=2, model="rig", seed=42)),
+                 ("single_dist", dict(n_markers=70, n_views=140, visibility=0.4, seed=43)),
+                 ("rig_dist", dict(n_markers=50, n_views=80, visibility=0.5, n_cam=2, model="rig", seed=44))):
     kw = dict(kw)
+    # *_dist: the distributed hand-written Cholesky (block columns over the ranks, panels broadcast) forced on a
+    # system of 3-4 panels; the others take the automatic choice (replicated cuSOLVER at this size)
+    if name.endswith("_dist"):
+        os.environ["RCC_CHOLESKY"] = "dist"
+    else:
+        os.environ.pop("RCC_CHOLESKY", None)
     scene = make_scene(kw.pop("n_markers"), kw.pop("n_views"), kw.pop("visibility"), **kw)
     opts = dict(max_iterations=30, function_tolerance=1e-14, gradient_tolerance=1e-12, parameter_tolerance=1e-13)
     dba = DistributedBA(scene, device=local)

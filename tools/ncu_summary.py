@@ -37,9 +37,14 @@ for n, hi in enumerate(his):
         if not toks:
             continue
         op = toks[1] if toks[0].startswith('@') and len(toks) > 1 else toks[0]
-        ns = int(r[ix['# Samples']] or 0); samples += ns
-        ie = int(r[ix['Instructions Executed']] or 0)
-        wf = int(r[ix['L1 Wavefronts Shared']] or 0); wi = int(r[ix['L1 Wavefronts Shared Ideal']] or 0)
+        def col(name):          # a kernel without shared-memory traffic has no wavefront columns on its source page
+            try:
+                return int(float(r[ix[name]] or 0)) if name in ix else 0
+            except ValueError:
+                return 0
+        ns = col('# Samples'); samples += ns
+        ie = col('Instructions Executed')
+        wf = col('L1 Wavefronts Shared'); wi = col('L1 Wavefronts Shared Ideal')
         parts = op.split('.')
         key = parts[0] + ('.' + '.'.join(parts[1:3]) if parts[0] in ('LDS', 'STS', 'LDG', 'STG', 'LDGSTS') else '')
         a = agg.setdefault(key, [0, 0, 0, 0]); a[0] += ie; a[1] += ns; a[2] += wf; a[3] += wi
