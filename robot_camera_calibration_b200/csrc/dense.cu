@@ -18,8 +18,9 @@
 //   chol_panel_kernel   64-row strips below the block: X <- X L_kk^-T by 32-column sub-steps
 //                       X_c <- (X_c - sum_{p<c} X_p L_cp^T) inv(L_cc)^T, all DMMA, the strip resident in shared memory.
 //   chol_update_kernel  trailing update C -= P P^T restricted to the block columns this rank owns: 128 x 64 tiles,
-//                       4 warps x (64 x 32) accumulators in registers, cp.async 4-stage pipeline over the 128-deep
-//                       panel, 2 CTAs per SM so that one CTA's tile load / write-back overlaps the other's MMAs.
+//                       8 warps x (32 x 32) accumulators in registers, cp.async 4-stage pipeline over the 128-deep
+//                       panel, 2 CTAs per SM (16 warps: the DMMA pipe needs ~4 warps per sub-partition to stay
+//                       full) so that one CTA's tile load / write-back overlaps the other's MMAs.
 #include "common.cuh"
 #include "dense.h"
 
@@ -41,6 +42,7 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
+// (mma.m16n8k8.f64 is no shortcut on sm_100a: ptxas lowers it to four DMMA.8x8x4.)
 // 16-byte global -> shared copy; bytes == 0 writes zeros without touching src
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -291,10 +293,15 @@ struct UpdateArgs {
   int i_tile0;              // first 128-row tile covered by blockIdx.x
 };
 
-__global__ void __launch_bounds__(128, 2) chol_update_kernel(const UpdateArgs a) {
+// 8 warps: warp (wm, wn) owns the 32 x 32 sub-tile at rows 32 wm, columns 32 wn of the CTA's 128 x 64 tile (16
+// accumulator tiles of 8 x 8 = 64 registers); 2 CTAs per SM = 4 warps per SM sub-partition.  A single warp cannot
+// issue DMMA.8x8x4 back to back (ptxas pads them: ~26 cycles between two of the same warp against 16 cycles of pipe
+// time each), so the FP64 pipe needs several resident warps per sub-partition to stay full -- with 2 (the first
+// version: 4 warps x 64 x 32) the kernel reached 58 % of the pipe's peak.
+__global__ void __launch_bounds__(256, 2) chol_update_kernel(const UpdateArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp & 1, wn = warp >> 1;
+  const int wm = warp & 3, wn = warp >> 2;
   const int jt = blockIdx.y;
   const int j0 = (a.first_blk + (jt >> 1) * a.blk_stride) * NB + (jt & 1) * UP_BN;
   const int i0 = (a.i_tile0 + blockIdx.x) * UP_BM;
@@ -304,16 +311,16 @@ __global__ void __launch_bounds__(128, 2) chol_update_kernel(const UpdateArgs a)
     double* as = sm + st * UP_STAGE_DOUBLES;
     double* bs = as + UP_BK * UP_AST;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int idx = tid + 128 * q;
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + 256 * q;
       const int kk = idx >> 6, mm = (idx & 63) * 2;
       const int kg = kc * UP_BK + kk;
       const bool ok = kg < a.kb && i0 + mm < a.n_rows;
       cp_async16(as + kk * UP_AST + mm, ok ? a.A + (size_t)(a.k0 + kg) * a.ld + i0 + mm : a.A, ok ? 16 : 0);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = tid + 128 * q;
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + 256 * q;
       const int kk = idx >> 5, nn = (idx & 31) * 2;
       const int kg = kc * UP_BK + kk;
       const bool ok = kg < a.kb && j0 + nn < a.n_rows;
@@ -325,65 +332,59 @@ __global__ void __launch_bounds__(128, 2) chol_update_kernel(const UpdateArgs a)
     if (s < nk) load(s, s);
     cp_async_commit();
   }
-  double acc[8][4][2] = {};
+  double acc[4][4][2] = {};
   const int lk = lane & 3, lr = lane >> 2;
   for (int kc = 0; kc < nk; ++kc) {
     cp_async_wait<UP_STAGES - 2>();
     __syncthreads();
     if (kc + UP_STAGES - 1 < nk) load(kc + UP_STAGES - 1, (kc + UP_STAGES - 1) % UP_STAGES);
     cp_async_commit();
-    const double* as = sm + (kc % UP_STAGES) * UP_STAGE_DOUBLES + wm * 64;
-    const double* bs = sm + (kc % UP_STAGES) * UP_STAGE_DOUBLES + UP_BK * UP_AST + wn * 32;
-    // fragments of k-step s+1 are loaded while the 32 MMAs of k-step s issue
-    double af[2][8], bf[2][4];
+    const double* as = sm + (kc % UP_STAGES) * UP_STAGE_DOUBLES + wm * 32 + lr;
+    const double* bs = sm + (kc % UP_STAGES) * UP_STAGE_DOUBLES + UP_BK * UP_AST + wn * 32 + lr;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) af[0][i] = as[lk * UP_AST + 8 * i + lr];
+    for (int k = 0; k < UP_BK; k += 4) {
+      double af[4], bf[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bf[0][j] = bs[lk * UP_BST + 8 * j + lr];
+      for (int i = 0; i < 4; ++i) af[i] = as[(k + lk) * UP_AST + 8 * i];
 #pragma unroll
-    for (int ks = 0; ks < UP_BK / 4; ++ks) {
-      const int cur = ks & 1, nxt = cur ^ 1;
-      if (ks + 1 < UP_BK / 4) {
+      for (int j = 0; j < 4; ++j) bf[j] = bs[(k + lk) * UP_BST + 8 * j];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) af[nxt][i] = as[(4 * (ks + 1) + lk) * UP_AST + 8 * i + lr];
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bf[nxt][j] = bs[(4 * (ks + 1) + lk) * UP_BST + 8 * j + lr];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(acc[i][j], af[cur][i], bf[cur][j]);
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
-  // C(i, j) -= acc, lower triangle only.  The tile comes from HBM (~0.8 us): 32 loads are put in flight before the
-  // first store, so the read-modify-write latency is paid twice per tile instead of once per column.
-  const int ib = i0 + wm * 64 + lr, jb = j0 + wn * 32 + 2 * lk;
+  // C(i, j) -= acc, lower triangle only.  The tile comes from HBM (~0.8 us): 16 loads per thread are in flight
+  // before the first store, so the read-modify-write latency is paid twice per tile, not once per element.
+  const int ib = i0 + wm * 32 + lr, jb = j0 + wn * 32 + 2 * lk;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    double cv[4][8];
+    double cv[4][2][2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int j = 2 * h + (c >> 1), q = c & 1;
-      const int col = jb + 8 * j + q;
-      const double* cp = a.A + (size_t)col * a.ld;
+    for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = ib + 8 * i;
-        cv[c][i] = (col < a.n_cols && row >= col && row < a.n_rows) ? cp[row] : 0.0;
+      for (int q = 0; q < 2; ++q) {
+        const int col = jb + 8 * (2 * h + jj) + q;
+        const double* cp = a.A + (size_t)col * a.ld;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = ib + 8 * i;
+          cv[i][jj][q] = (col < a.n_cols && row >= col && row < a.n_rows) ? cp[row] : 0.0;
+        }
       }
-    }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int j = 2 * h + (c >> 1), q = c & 1;
-      const int col = jb + 8 * j + q;
-      double* cp = a.A + (size_t)col * a.ld;
+    for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = ib + 8 * i;
-        if (col < a.n_cols && row >= col && row < a.n_rows) cp[row] = cv[c][i] - acc[i][j][q];
+      for (int q = 0; q < 2; ++q) {
+        const int col = jb + 8 * (2 * h + jj) + q;
+        double* cp = a.A + (size_t)col * a.ld;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = ib + 8 * i;
+          if (col < a.n_cols && row >= col && row < a.n_rows) cp[row] = cv[i][jj][q] - acc[i][2 * h + jj][q];
+        }
       }
-    }
   }
 }
 
@@ -416,7 +417,7 @@ void chol_update(double* A, int ld, int n_rows, int n_cols, int k0, int kb, int 
   const size_t smem = (size_t)UP_STAGES * UP_STAGE_DOUBLES * sizeof(double);
   g_update_optin.ensure(chol_update_kernel, smem);
   dim3 grid(ceil_div(n_rows, UP_BM) - a.i_tile0, 2 * n_blks);
-  chol_update_kernel<<<grid, 128, smem, s>>>(a);
+  chol_update_kernel<<<grid, 256, smem, s>>>(a);
   RCC_CUDA(cudaGetLastError());
 }
 
