@@ -290,8 +290,26 @@ struct UpdateArgs {
   int ld, n_rows, n_cols;   // rows 0 .. n_rows-1 exist; columns >= n_cols are never updated
   int k0, kb;               // panel
   int first_blk, blk_stride;  // block columns first_blk, first_blk + blk_stride, ... (128 wide)
-  int i_tile0;              // first 128-row tile covered by blockIdx.x
+  int n_tiles_m;            // 128-row tiles of the whole matrix: ceil(n_rows / 128)
 };
+
+// CTA id -> (block column b, 64-column half, 128-row tile) over the lower-triangular part only: block column b
+// (global block index t_b = first_blk + b * blk_stride) has n_tiles_m - t_b row tiles, each split into two halves.
+// P(b) = CTAs before block column b = 2 [b A - S b (b - 1) / 2],  A = n_tiles_m - first_blk,  S = blk_stride.
+__device__ __forceinline__ void update_tile_of(const UpdateArgs& a, int id, int& j0, int& i0) {
+  const double A = (double)(a.n_tiles_m - a.first_blk), S = (double)a.blk_stride;
+  const double disc = (2.0 * A + S) * (2.0 * A + S) - 4.0 * S * (double)id;
+  int b = (int)(((2.0 * A + S) - sqrt(fmax(disc, 0.0))) / (2.0 * S));
+  auto P = [&](int bb) { return 2 * (bb * (a.n_tiles_m - a.first_blk) - a.blk_stride * ((bb * (bb - 1)) / 2)); };
+  while (b > 0 && P(b) > id) --b;
+  while (P(b + 1) <= id) ++b;
+  const int tb = a.first_blk + b * a.blk_stride;
+  const int cnt = a.n_tiles_m - tb;
+  const int rem = id - P(b);
+  const int half = rem / cnt, it = rem - half * cnt;
+  j0 = tb * NB + half * UP_BN;
+  i0 = (tb + it) * UP_BM;
+}
 
 // 8 warps: warp (wm, wn) owns the 32 x 32 sub-tile at rows 32 wm, columns 32 wn of the CTA's 128 x 64 tile (16
 // accumulator tiles of 8 x 8 = 64 registers); 2 CTAs per SM = 4 warps per SM sub-partition.  A single warp cannot
@@ -302,11 +320,19 @@ __global__ void __launch_bounds__(256, 2) chol_update_kernel(const UpdateArgs a)
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 3, wn = warp >> 2;
-  const int jt = blockIdx.y;
-  const int j0 = (a.first_blk + (jt >> 1) * a.blk_stride) * NB + (jt & 1) * UP_BN;
-  const int i0 = (a.i_tile0 + blockIdx.x) * UP_BM;
-  if (j0 >= a.n_cols || i0 >= a.n_rows || i0 + UP_BM <= j0) return;   // outside / strictly above the diagonal
+  int j0, i0;
+  update_tile_of(a, blockIdx.x, j0, i0);
+  if (j0 >= a.n_cols || i0 >= a.n_rows) return;   // the second half of a last, narrow block column
   const int nk = (a.kb + UP_BK - 1) / UP_BK;
+  // the C tile is read-modify-written at the very end: start it on its way from HBM to L2 now (2 lines per thread)
+  {
+    const int col = j0 + (tid >> 2), r = i0 + (tid & 3) * 32;
+    if (col < a.n_cols && r < a.n_rows) {
+      const double* pc = a.A + (size_t)col * a.ld + r;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pc));
+      if (r + 16 < a.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 16));
+    }
+  }
   auto load = [&](int kc, int st) {
     double* as = sm + st * UP_STAGE_DOUBLES;
     double* bs = as + UP_BK * UP_AST;
@@ -413,11 +439,15 @@ void chol_panel(double* A, int ld, int n_rows, int k0, int kb, const double* ws,
 void chol_update(double* A, int ld, int n_rows, int n_cols, int k0, int kb, int first_blk, int blk_stride, int n_blks,
                  cudaStream_t s) {
   if (n_blks <= 0 || first_blk * NB >= n_cols) return;
-  UpdateArgs a{A, ld, n_rows, n_cols, k0, kb, first_blk, blk_stride, (first_blk * NB) / UP_BM};
+  static_assert(NB == UP_BM, "row tiles and block columns share one index");
+  const int tm = ceil_div(n_rows, UP_BM);
+  UpdateArgs a{A, ld, n_rows, n_cols, k0, kb, first_blk, blk_stride, tm};
   const size_t smem = (size_t)UP_STAGES * UP_STAGE_DOUBLES * sizeof(double);
   g_update_optin.ensure(chol_update_kernel, smem);
-  dim3 grid(ceil_div(n_rows, UP_BM) - a.i_tile0, 2 * n_blks);
-  chol_update_kernel<<<grid, 256, smem, s>>>(a);
+  // lower-triangular tiles only: block column b has tm - (first_blk + b * stride) row tiles, two halves each
+  const int64_t n_ctas = 2 * ((int64_t)n_blks * (tm - first_blk) - (int64_t)blk_stride * n_blks * (n_blks - 1) / 2);
+  if (n_ctas <= 0) return;
+  chol_update_kernel<<<(unsigned)n_ctas, 256, smem, s>>>(a);
   RCC_CUDA(cudaGetLastError());
 }
 
