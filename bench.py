@@ -172,7 +172,9 @@ class CpuWorkload:
         os.environ["OMP_NUM_THREADS"] = str(threads)           # before libgomp is loaded
         os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import cpu_baseline
         from cpu_baseline import CpuBA
+        cpu_baseline.set_num_threads(threads)                  # torchrun's OMP_NUM_THREADS=1 was read at load time
         self.slices, self.n_blocks = [], 0
         self.desc = self.views = None
         for lo, hi in ranges:

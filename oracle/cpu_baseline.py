@@ -39,6 +39,7 @@ def load():
         lib.cpu_ba_create.restype = C.c_void_p
         lib.cpu_ba_create.argtypes = [C.c_int] * 4 + [C.c_int64, C.c_int, _ip, _ip, _ip, _dp]
         lib.cpu_ba_destroy.argtypes = [C.c_void_p]
+        lib.cpu_ba_set_num_threads.argtypes = [C.c_int]
         lib.cpu_ba_set_params.argtypes = [C.c_void_p] + [_dp] * 6
         lib.cpu_ba_evaluate.argtypes = [C.c_void_p, C.c_int]
         lib.cpu_ba_linearize.argtypes = [C.c_void_p, _dp]
@@ -51,6 +52,11 @@ def load():
 
 def _p(a, t=_dp):
     return None if a is None else a.ctypes.data_as(t)
+
+
+def set_num_threads(n):
+    """Size of the OpenMP team of the restatement (the environment variable is too late once libgomp is loaded)."""
+    load().cpu_ba_set_num_threads(int(n))
 
 
 class CpuBA:

@@ -303,6 +303,9 @@ inline void fwd6(const double* L, double* X, int ncol, int ld) {
 extern "C" {
 
 int cpu_ba_num_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 and libgomp has read it long before this library is loaded: the CPU arm
+// sets the team size at run time instead
+void cpu_ba_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 void* cpu_ba_create(int rig, int n_views, int n_markers, int n_cam, int64_t n, int elim_view, const int32_t* vi,
                     const int32_t* mi, const int32_t* ci, const double* pix) {

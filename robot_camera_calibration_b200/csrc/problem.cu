@@ -630,10 +630,12 @@ static int cholesky_mode(P_t* P) {
   else if (s == "own") mode = 1;
   else if (s == "dist") mode = multi ? 2 : 1;
   else {
-    // auto: the hand-written factorisation pays off where its trailing update dominates; below that the panel
-    // latency of 128-column steps loses to cuSOLVER (measured)
+    // auto: with several ranks and a system large enough for its trailing update to dominate, the hand-written
+    // factorisation distributed over the ranks; on one GPU it runs at 86 % of cusolverDnDpotrf's rate at n = 30 009
+    // and loses to it below (panel latency of the 128-column steps), so a single rank calls the library
+    // (measured)
     const int n_min = env_int("RCC_CHOL_MIN_N", 6000);
-    mode = P->n_red >= n_min ? (multi ? 2 : 1) : 0;
+    mode = (multi && P->n_red >= n_min) ? 2 : 0;
   }
   P->chol_mode = mode;
   return mode;
