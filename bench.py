@@ -265,6 +265,7 @@ def multi_gpu_parity(torch, dist, rank, world, local):
     for name, chol, kw in cases:
         kw = dict(kw)
         os.environ["RCC_CHOLESKY"] = chol
+        os.environ["RCC_PACK_MIN_N"] = "0" if chol == "dist" else "1000000"     # packed-triangle all-reduce, like cfg4
         scene = make_scene(kw.pop("n_markers"), kw.pop("n_views"), kw.pop("visibility"), **kw)
         local_scene, (lo, hi) = shard_scene(scene, rank, world, "views")
         gp = BAProblem.from_scene(local_scene, device=local, eliminate="views")
@@ -312,6 +313,7 @@ def multi_gpu_parity(torch, dist, rank, world, local):
                          "converged_views_max_abs": float(np.abs(views_all - v1).max()),
                          "converged_markers_max_abs": float(np.abs(markers_n - m1).max())}
         dist.barrier()
+    os.environ.pop("RCC_PACK_MIN_N", None)
     if saved is None:
         os.environ.pop("RCC_CHOLESKY", None)
     else:

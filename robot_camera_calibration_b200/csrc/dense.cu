@@ -481,6 +481,7 @@ void CholDriver::destroy() {
     if (e) cudaEventDestroy(e);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ws) cudaFree(ws);
+  if (stage) cudaFree(stage);
   if (info) cudaFree(info);
   *this = CholDriver();
 }
@@ -496,6 +497,12 @@ void chol_factor(double* A, int n, int ld, int n_rows, int rank, int n_ranks, nc
   }
   const int nblk = (n + CHOL_NB - 1) / CHOL_NB;
   cudaStream_t ps = d.panel_stream;
+  if (n_ranks > 1 && d.stage_cap < (size_t)n_rows * CHOL_NB) {
+    if (d.stage) RCC_CUDA(cudaFree(d.stage));
+    d.stage = nullptr;
+    d.stage_cap = (size_t)n_rows * CHOL_NB;
+    RCC_CUDA(cudaMalloc(&d.stage, d.stage_cap * sizeof(double)));
+  }
   RCC_CUDA(cudaEventRecord(d.ev_fork, main));
   RCC_CUDA(cudaStreamWaitEvent(ps, d.ev_fork, 0));
   RCC_CUDA(cudaMemsetAsync(d.info, 0, sizeof(int), ps));
@@ -510,12 +517,20 @@ void chol_factor(double* A, int n, int ld, int n_rows, int rank, int n_ranks, nc
       d.launches += 2;
     }
     if (n_ranks > 1) {
-      // rows k0 .. k0+kb-1 of the row-major buffer from the diagonal on = the panel (+ the unused strict upper part
-      // of the following rows): one contiguous range, broadcast in place
+      // The panel = rows k0 .. k0+kb-1 of the row-major buffer from column k0 on.  In place that is one contiguous
+      // range only together with the unused strict upper part of the rows in between (30 MB per panel whatever
+      // k0 is); packed through a staging buffer it is kb x (n_rows - k0): half the bytes on average, and the late
+      // panels -- the ones on the critical path of the ranks -- become latency-sized.
+      const size_t width = (size_t)(n_rows - k0);
       double* p = A + (size_t)k0 * ld + k0;
-      const size_t count = (size_t)(kb - 1) * ld + (size_t)(n_rows - k0);
-      ncclResult_t r = ncclBroadcast(p, p, count, ncclDouble, owner, comm, ps);
+      if (owner == rank)
+        RCC_CUDA(cudaMemcpy2DAsync(d.stage, width * sizeof(double), p, (size_t)ld * sizeof(double),
+                                   width * sizeof(double), kb, cudaMemcpyDeviceToDevice, ps));
+      ncclResult_t r = ncclBroadcast(d.stage, d.stage, width * kb, ncclDouble, owner, comm, ps);
       if (r != ncclSuccess) throw Error(RCC_NCCL_ERROR, std::string("ncclBroadcast(panel): ") + ncclGetErrorString(r));
+      if (owner != rank)
+        RCC_CUDA(cudaMemcpy2DAsync(p, (size_t)ld * sizeof(double), d.stage, width * sizeof(double),
+                                   width * sizeof(double), kb, cudaMemcpyDeviceToDevice, ps));
     }
     RCC_CUDA(cudaEventRecord(d.ev_panel[K & 3], ps));
     RCC_CUDA(cudaStreamWaitEvent(main, d.ev_panel[K & 3], 0));

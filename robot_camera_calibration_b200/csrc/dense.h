@@ -30,6 +30,8 @@ struct CholDriver {
   cudaEvent_t ev_col[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   double* ws = nullptr;
+  double* stage = nullptr;               // packed panel of the broadcast (kb x rows-below-and-including-the-diagonal)
+  size_t stage_cap = 0;                  // doubles
   int* info = nullptr;                   // device
   int64_t launches = 0;                  // kernels launched so far (for rcc_ba_launch_count)
   void init();

@@ -647,8 +647,20 @@ static void do_step(P_t* P) {
   const int n = P->n_red;
   if (P->comm) {
     Scoped t(P, ST_ALLREDUCE, 1);
-    const size_t count = (size_t)n * P->ld + 2 * (size_t)n + 8;
-    RCC_NCCL(ncclAllReduce(P->S.p, P->S.p, count, ncclDouble, ncclSum, P->comm, P->stream));
+    const size_t tail = 2 * (size_t)n + 8;
+    if (n >= env_int("RCC_PACK_MIN_N", 6000)) {
+      // half of the square buffer is the dead lower triangle: pack the rows' live parts, reduce 3.6 GB instead of
+      // 7.2 GB (cfg4), unpack; the two copies cost ~2.5 ms of HBM time against ~8 ms of link time saved
+      const size_t count = packed_upper_doubles(n, P->ld, tail);
+      P->packed_S.ensure(count);
+      launch_pack_upper(P->S.p, n, P->ld, tail, P->packed_S.p, true, P->stream);
+      RCC_NCCL(ncclAllReduce(P->packed_S.p, P->packed_S.p, count, ncclDouble, ncclSum, P->comm, P->stream));
+      launch_pack_upper(P->S.p, n, P->ld, tail, P->packed_S.p, false, P->stream);
+      P->launch_count += 2;
+    } else {
+      const size_t count = (size_t)n * P->ld + tail;
+      RCC_NCCL(ncclAllReduce(P->S.p, P->S.p, count, ncclDouble, ncclSum, P->comm, P->stream));
+    }
   }
   {
     Scoped t(P, ST_MASK, 3);

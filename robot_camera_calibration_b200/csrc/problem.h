@@ -93,7 +93,7 @@ struct rcc_ba_problem {
 
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
-  rcc::DBuf<double> potrf_work;
+  rcc::DBuf<double> potrf_work, packed_S;   // packed_S: upper triangle + tail for the all-reduce (multi-rank, large n)
   rcc::DBuf<int> dev_info;
   int potrf_lwork = 0;
 

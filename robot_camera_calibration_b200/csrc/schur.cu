@@ -775,6 +775,33 @@ void launch_apply(const double* x, const double* d, double* out, int64_t n, cuda
   RCC_CUDA(cudaGetLastError());
 }
 
+size_t packed_upper_doubles(int32_t n, int32_t ld, size_t tail) {
+  return (size_t)n * ld - (size_t)n * (n - 1) / 2 + tail;
+}
+// one CTA per row (the last CTA takes the tail); rows are contiguous on both sides
+__global__ void __launch_bounds__(256) pack_upper_kernel(double* __restrict__ S, int n, int ld, size_t tail,
+                                                         double* __restrict__ packed, bool to_packed) {
+  const int j = blockIdx.x;
+  double* a;
+  double* b;
+  size_t len;
+  if (j < n) {
+    a = S + (size_t)j * ld + j;
+    b = packed + ((size_t)j * ld - (size_t)j * (j - 1) / 2);
+    len = (size_t)(ld - j);
+  } else {
+    a = S + (size_t)n * ld;
+    b = packed + ((size_t)n * ld - (size_t)n * (n - 1) / 2);
+    len = tail;
+  }
+  if (to_packed) for (size_t i = threadIdx.x; i < len; i += 256) b[i] = a[i];
+  else for (size_t i = threadIdx.x; i < len; i += 256) a[i] = b[i];
+}
+void launch_pack_upper(double* S, int32_t n, int32_t ld, size_t tail, double* packed, bool to_packed, cudaStream_t s) {
+  pack_upper_kernel<<<n + 1, 256, 0, s>>>(S, n, ld, tail, packed, to_packed);
+  RCC_CUDA(cudaGetLastError());
+}
+
 __global__ void symmetrize_kernel(double* S, int n, int ld) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;  // column
   const int i = blockIdx.y;                             // row
