@@ -47,7 +47,9 @@ FLOP_PRODUCTS_ALL = 2 * 8 * 253           # J^T J / J^T r: 253 distinct entries 
 FLOP_PRODUCTS_E = 2 * 8 * 172             # E pass alone: OO, OT, O x [S r], [S r] x [S r]
 FLOP_PER_BLOCK = FLOP_PRODUCTS_ALL + FLOP_EVAL_PER_BLOCK
 FLOP_PER_BLOCK_E = FLOP_PRODUCTS_E + FLOP_EVAL_PER_BLOCK
-NCU_DRAM_BYTES_E_PASS_CFG2 = 32313856 + 89391616   # measured once under ncu (cfg2, 454 996 blocks)
+# dram__bytes_read.sum + dram__bytes_write.sum of one E-pass launch, measured once under `ncu --set full`:
+NCU_DRAM_BYTES_E_PASS = {2: 32313856 + 89391616,       # cfg2, 454 996 blocks  (profiles/r1_ncu_full_summary.txt)
+                         4: 819874048 + 3662994000}    # cfg4, 11 880 665 blocks (profiles/r2_ncu_k2_cfg4_summary.txt)
 
 CONFIGS = {
     # cfg: (tags, views, visibility, seed, views per generator chunk, description)
@@ -565,9 +567,10 @@ def run_ours(args):
                   "rule": "contiguous keyframe ranges by eliminated-block owner; no data-path collective in `value`"},
         "roofline": {"bound": "hbm", "kernel": "assemble_kernel<E pass> (fused residual+Jacobian+J^T J tiles), rank 0",
                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                     "traffic": NCU_DRAM_BYTES_E_PASS_CFG2 if (args.config == 2 and world == 1 and args.scale == 1.0) else None,
+                     "traffic": NCU_DRAM_BYTES_E_PASS.get(args.config) if (world == 1 and args.scale == 1.0) else None,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one E-pass launch "
-                                       "(cfg2: profiles/r1_ncu_full_summary.txt; see profiles/ for this round's captures)",
+                                       "on this workload (profiles/r2_ncu_k2_cfg4_summary.txt; cfg2: "
+                                       "profiles/r1_ncu_full_summary.txt); N = 1 only",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_BLOCK_E * n_blocks,
                      "kernel_ms": k_ms, "f_pass_kernel_ms": kf_ms,

@@ -9,6 +9,26 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 scene, desc, _ = workload(cfg, 0, 1, scale)
+if os.environ.get("RCC_MORTON") == "1":
+    # experiment: relabel the tags along a Morton curve of their positions (what would the SYRK gain from an
+    # ordering in which every keyframe's tags are contiguous runs?)
+    import numpy as np
+    t = scene.markers[:, 3:6]
+    q = ((t - t.min(0)) / np.maximum(t.max(0) - t.min(0), 1e-12) * 1023).astype(np.int64)
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF0000FF
+        v = (v | (v << 8)) & 0x0300F00F00F00F
+        v = (v | (v << 4)) & 0x030C30C30C30C3
+        v = (v | (v << 2)) & 0x09249249249249
+        return v
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    code[0] = -1                                   # the world tag stays first
+    order = np.argsort(code, kind="stable")        # new -> old
+    inv = np.empty_like(order); inv[order] = np.arange(len(order))
+    scene.markers, scene.sizes = scene.markers[order], scene.sizes[order]
+    scene.const_markers = scene.const_markers[order]
+    scene.marker_idx = inv[scene.marker_idx].astype(np.int32)
+    desc += " [tags relabelled in Morton order]"
 gp = BAProblem.from_scene(scene, eliminate="views")
 gp.linearize(want_cost=False)
 for _ in range(2):
