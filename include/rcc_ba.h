@@ -118,7 +118,7 @@ int rcc_ba_set_observations(rcc_ba_problem* p, const int32_t* view_idx, const in
 /* replace the pixel coordinates only (same indices, caller order).  Asynchronous: `pixels` must stay
  * valid until the next call that returns results (linearize with a cost pointer, evaluate, any getter).
  * When the caller order is the sorted order (blocks listed per eliminated block) the copy runs on a side
- * stream in 4 pieces and the next rcc_ba_linearize starts the E pass of a piece as soon as it has landed:
+ * streams in 8 pieces (each piece also lands in the second sorted copy) and the next rcc_ba_linearize starts the E pass of a piece as soon as it has landed:
  * call the parameter setters BEFORE update_pixels so that they do not queue behind it.  Otherwise: one
  * H2D copy plus a device-side permutation into the sorted layouts. */
 int rcc_ba_update_pixels(rcc_ba_problem* p, const double* pixels /*n_obs_blocks x 8*/);

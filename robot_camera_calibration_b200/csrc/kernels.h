@@ -280,6 +280,10 @@ void launch_apply(const double* x, const double* d, double* out, int64_t n, cuda
 void launch_symmetrize(double* S, int32_t n, int32_t ld, cudaStream_t s);
 // gather pixels from caller order into a sorted order
 void launch_permute_pixels(const double* src, const int32_t* orig, double* dst, int64_t n, cudaStream_t s);
+// one piece of an upload in sorted order: e_pix[g] = (double) src16[g] (src16 == nullptr: e_pix already holds the
+// piece) and f_pix[f_inv[g]] = e_pix[g], so that the F-sorted copy is complete when the last piece has landed
+void launch_scatter_pixels(const int16_t* src16, double* e_pix, const int32_t* f_inv, double* f_pix, int64_t n,
+                           cudaStream_t s);
 // integer pixels -> FP64: dst[g] = (double) src[orig ? orig[g] : g]  for blocks g in [0, n)
 void launch_convert_pixels_i16(const int16_t* src, const int32_t* orig, double* dst, int64_t n, cudaStream_t s);
 // write a scratch buffer (L2 flush)

@@ -324,6 +324,16 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
     }
     P->f_oth.upload(oth, s);
     P->f_orig.upload(perm_f, s);
+    {
+      // E-sorted position -> F-sorted position (the piecewise uploads scatter every piece into f_pix as it lands)
+      std::vector<int32_t> e_pos_of_caller((size_t)n), f_inv((size_t)n);
+#pragma omp parallel for
+      for (int64_t i = 0; i < n; ++i) e_pos_of_caller[perm_e[i]] = (int32_t)i;
+#pragma omp parallel for
+      for (int64_t i = 0; i < n; ++i) f_inv[e_pos_of_caller[perm_f[i]]] = (int32_t)i;
+      P->f_inv.upload(f_inv, s);
+      RCC_CUDA(cudaStreamSynchronize(s));
+    }
     P->f_pix.upload(pix, s);
     RCC_CUDA(cudaStreamSynchronize(s));
   }
@@ -466,12 +476,10 @@ static void ensure_expanded(P_t* P) {
   P->expanded_valid = true;
 }
 
-// after a piecewise update_pixels: wait for the last piece and bring f_pix up to date
+// after a piecewise update_pixels: wait for the last piece (every piece has scattered itself into f_pix)
 static void ensure_pixels(P_t* P) {
   if (!P->pix_pending) return;
   for (int k = 0; k < rcc_ba_problem::PIX_PIECES; ++k) RCC_CUDA(cudaStreamWaitEvent(P->stream, P->ev_piece[k], 0));
-  launch_permute_pixels(P->e_pix.p, P->f_orig.p, P->f_pix.p, P->n_obs, P->stream);
-  P->launch_count += 1;
   P->pix_pending = false;
 }
 
@@ -1151,9 +1159,12 @@ int rcc_ba_update_pixels(rcc_ba_problem* P, const double* pixels) {
       // pieces alternate between two streams: two copy engines in flight keep the link busier (48 -> 52 GB/s)
       cudaStream_t cs = (k & 1) ? P->side_stream2 : P->side_stream;
       const int64_t b0 = P->piece_block[k], b1 = P->piece_block[k + 1];
-      if (b1 > b0)
+      if (b1 > b0) {
         RCC_CUDA(cudaMemcpyAsync(P->e_pix.p + b0 * 8, pixels + b0 * 8, (size_t)(b1 - b0) * 8 * sizeof(double),
                                  cudaMemcpyHostToDevice, cs));
+        launch_scatter_pixels(nullptr, P->e_pix.p + b0 * 8, P->f_inv.p + b0, P->f_pix.p, b1 - b0, cs);
+        P->launch_count += 1;
+      }
       RCC_CUDA(cudaEventRecord(P->ev_piece[k], cs));
     }
     P->pix_pending = true;
@@ -1199,7 +1210,7 @@ int rcc_ba_update_pixels_i16(rcc_ba_problem* P, const int16_t* pixels) {
       if (b1 > b0) {
         RCC_CUDA(cudaMemcpyAsync(P->pix_i16.p + b0 * 8, pixels + b0 * 8, (size_t)(b1 - b0) * 8 * sizeof(int16_t),
                                  cudaMemcpyHostToDevice, cs));
-        launch_convert_pixels_i16(P->pix_i16.p + b0 * 8, nullptr, P->e_pix.p + b0 * 8, b1 - b0, cs);
+        launch_scatter_pixels(P->pix_i16.p + b0 * 8, P->e_pix.p + b0 * 8, P->f_inv.p + b0, P->f_pix.p, b1 - b0, cs);
       }
       RCC_CUDA(cudaEventRecord(P->ev_piece[k], cs));
     }

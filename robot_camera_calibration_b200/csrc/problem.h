@@ -56,9 +56,9 @@ struct rcc_ba_problem {
   // piecewise pixel upload (rcc_ba_update_pixels when the caller order is the E-sorted order): the H2D
   // copy runs on the side stream in PIX_PIECES pieces cut at chunk boundaries, and the next linearize
   // starts the E pass of a piece as soon as that piece has landed
-  static constexpr int PIX_PIECES = 4;
+  static constexpr int PIX_PIECES = 8;
   bool pix_identity = false;         // e_orig is the identity permutation
-  bool pix_pending = false;          // pieces in flight; f_pix not yet permuted
+  bool pix_pending = false;          // pieces in flight on the copy streams (each piece also scatters itself into f_pix)
   int piece_chunk[PIX_PIECES + 1] = {0};
   int64_t piece_block[PIX_PIECES + 1] = {0};
   cudaEvent_t ev_piece[PIX_PIECES] = {nullptr};
@@ -73,7 +73,7 @@ struct rcc_ba_problem {
   bool const_dirty = true;
 
   // observation blocks, E-sorted and F-sorted
-  rcc::DBuf<int32_t> e_own, e_oth, e_cam, e_orig, f_oth, f_orig, e_chunk_ptr, f_chunk_ptr;
+  rcc::DBuf<int32_t> e_own, e_oth, e_cam, e_orig, f_oth, f_orig, f_inv, e_chunk_ptr, f_chunk_ptr;   // f_inv: E-sorted -> F-sorted position
   rcc::DBuf<double> e_pix, f_pix, pix_staging;
   rcc::DBuf<int16_t> pix_i16;        // device staging of rcc_ba_update_pixels_i16
   rcc::DBuf<rcc::Chunk> e_chunks, f_chunks;

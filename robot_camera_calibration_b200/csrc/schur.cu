@@ -845,6 +845,30 @@ void launch_convert_pixels_i16(const int16_t* src, const int32_t* orig, double* 
   RCC_CUDA(cudaGetLastError());
 }
 
+// one thread per corner: 16-byte records on both sides; the F-sorted side is a scatter of whole 64-byte blocks
+__global__ void scatter_pixels_kernel(const int16_t* __restrict__ src16, double* __restrict__ e_pix,
+                                      const int32_t* __restrict__ f_inv, double* __restrict__ f_pix, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 4) return;
+  const int64_t g = i >> 2;
+  const int q = (int)(i & 3);
+  double2 v;
+  if (src16) {
+    const short2 s = reinterpret_cast<const short2*>(src16 + g * 8)[q];
+    v = make_double2((double)s.x, (double)s.y);
+    reinterpret_cast<double2*>(e_pix + g * 8)[q] = v;
+  } else {
+    v = reinterpret_cast<const double2*>(e_pix + g * 8)[q];
+  }
+  reinterpret_cast<double2*>(f_pix + (int64_t)f_inv[g] * 8)[q] = v;
+}
+void launch_scatter_pixels(const int16_t* src16, double* e_pix, const int32_t* f_inv, double* f_pix, int64_t n,
+                           cudaStream_t s) {
+  if (n == 0) return;
+  scatter_pixels_kernel<<<ceil_div(n * 4, 256), 256, 0, s>>>(src16, e_pix, f_inv, f_pix, n);
+  RCC_CUDA(cudaGetLastError());
+}
+
 __global__ void fill_kernel(double* p, int64_t n, double v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
