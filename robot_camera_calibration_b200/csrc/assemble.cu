@@ -102,8 +102,9 @@ assemble_kernel(const AssembleArgs a) {
   constexpr int PART = EPASS ? PG::PART_E : PG::PART_F;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk_id = blockIdx.x * PG::WARPS + warp;
-  if (chunk_id >= a.n_chunks) return;  // whole warp leaves together
+  const int launch_pos = blockIdx.x * PG::WARPS + warp;
+  if (launch_pos >= a.n_chunks) return;  // whole warp leaves together
+  const int chunk_id = a.chunk_list ? a.chunk_list[launch_pos] : launch_pos;
   double* wsm = smem + warp * WS::TOTAL;
   double* rows = wsm;                 // [BPW][8 rows][RS]
   double* stage = wsm + WS::STAGE;    // [2][BPW][POSEX] expanded pose of the other block, double buffered

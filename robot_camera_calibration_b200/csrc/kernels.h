@@ -57,7 +57,8 @@ struct AssembleArgs {
   const int32_t* oth;     // [n] index of the other 6-dof block
   const double* pix;      // [n*8]
   const Chunk* chunks;    // [n_chunks]
-  int32_t n_chunks;
+  int32_t n_chunks;       // chunks this launch covers
+  const int32_t* chunk_list;  // optional: the launch covers chunks chunk_list[0 .. n_chunks) instead of 0 .. n_chunks
   // parameters
   const double* view_x;   // expanded poses [n_views*24]
   const double* marker_x; // [n_markers*24]

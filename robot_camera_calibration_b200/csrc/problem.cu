@@ -191,8 +191,11 @@ static std::vector<int32_t> sort_by_owner(const int32_t* own, const int32_t* oth
   return perm;
 }
 
+// group_of (optional): a group id per sorted position, non-decreasing inside a (own, camera) run; chunks never
+// straddle a group boundary (the upload pieces of the F pass)
 static void make_chunks(const std::vector<int32_t>& perm, const std::vector<int32_t>& seg_ptr, const int32_t* cam,
-                        int n_own, int bpw, int ch_max, std::vector<Chunk>& chunks, std::vector<int32_t>& chunk_ptr) {
+                        int n_own, int bpw, int ch_max, std::vector<Chunk>& chunks, std::vector<int32_t>& chunk_ptr,
+                        const std::vector<int32_t>* group_of = nullptr) {
   chunks.clear();
   chunk_ptr.assign((size_t)n_own + 1, 0);
   for (int s = 0; s < n_own; ++s) {
@@ -201,7 +204,7 @@ static void make_chunks(const std::vector<int32_t>& perm, const std::vector<int3
     while (i < end) {
       const int c = cam[perm[i]];
       int j = i;
-      while (j < end && cam[perm[j]] == c) ++j;
+      while (j < end && cam[perm[j]] == c && (!group_of || (*group_of)[j] == (*group_of)[i])) ++j;
       const int len = j - i;
       const int nch = (len + ch_max - 1) / ch_max;
       int per = (len + nch - 1) / nch;
@@ -288,14 +291,18 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
     for (int64_t i = 0; i < n && ident; ++i) ident = perm_e[i] == (int32_t)i;
     P->pix_identity = ident && n > 0;
     P->pix_pending = false;
-    const int nc = P->n_chunks_e;
+    // pieces are cut at eliminated-block boundaries: 8 for large uploads (what is left after the copy is the work
+    // of the last piece: keep it short), 4 for small ones, where a piece must still be worth a launch
+    const int np = n >= 4000000 ? rcc_ba_problem::PIX_PIECES : 4;
     P->piece_chunk[0] = 0;
     P->piece_block[0] = 0;
+    int e_cut = 0;
     for (int k = 1; k <= rcc_ba_problem::PIX_PIECES; ++k) {
-      int c = (int)((int64_t)nc * k / rcc_ba_problem::PIX_PIECES);
-      c = std::max(c, P->piece_chunk[k - 1]);
-      P->piece_chunk[k] = (k == rcc_ba_problem::PIX_PIECES) ? nc : c;
-      P->piece_block[k] = (P->piece_chunk[k] >= nc) ? n : (int64_t)chunks[P->piece_chunk[k]].start;
+      const int64_t want = n * std::min(k, np) / np;
+      while (e_cut < P->n_e && seg_e[e_cut] < want) ++e_cut;      // first eliminated block starting at or after `want`
+      if (k >= np) e_cut = P->n_e;
+      P->piece_block[k] = seg_e[e_cut];
+      P->piece_chunk[k] = chunk_ptr[e_cut];
     }
   }
   {
@@ -306,7 +313,29 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
 
   // ---- F pass order
   std::vector<int32_t> perm_f = sort_by_owner(f_of, e_of, cam_idx, n, P->n_f, seg_f);
-  make_chunks(perm_f, seg_f, cam_idx, P->n_f, bpw, ch_max, chunks, chunk_ptr);
+  {
+    // F-pass chunks never straddle an upload piece: the F pass of a piece can then run as soon as the piece has
+    // landed, like its E pass (rows are sorted by eliminated block inside a camera run, pieces are ranges of them)
+    std::vector<int32_t> piece_of_e((size_t)P->n_e, 0), group((size_t)n, 0);
+    if (P->pix_identity) {
+      for (int k = 0, e = 0; k < rcc_ba_problem::PIX_PIECES; ++k)
+        for (; e < P->n_e && seg_e[e] < P->piece_block[k + 1]; ++e) piece_of_e[e] = k;
+#pragma omp parallel for
+      for (int64_t i = 0; i < n; ++i) group[i] = piece_of_e[e_of[perm_f[i]]];
+    }
+    make_chunks(perm_f, seg_f, cam_idx, P->n_f, bpw, ch_max, chunks, chunk_ptr, P->pix_identity ? &group : nullptr);
+    std::vector<int32_t> plist;
+    plist.reserve(chunks.size());
+    for (int k = 0; k < rcc_ba_problem::PIX_PIECES; ++k) {
+      P->f_piece_ptr[k] = (int)plist.size();
+      if (P->pix_identity)
+        for (size_t c = 0; c < chunks.size(); ++c)
+          if (group[chunks[c].start] == k) plist.push_back((int32_t)c);
+    }
+    P->f_piece_ptr[rcc_ba_problem::PIX_PIECES] = (int)plist.size();
+    if (plist.empty()) plist.push_back(0);
+    P->f_piece_list.upload(plist, s);
+  }
   P->n_chunks_f = (int)chunks.size();
   P->f_chunks.upload(chunks, s);
   P->f_chunk_ptr.upload(chunk_ptr, s);
@@ -488,6 +517,7 @@ static void do_linearize(P_t* P) {
   ensure_expanded(P);
   RCC_CUDA(cudaMemsetAsync(P->fail_flag.p, 0, sizeof(int32_t), P->stream));
   AssembleArgs a{};
+  bool f_done = false;
   a.view_x = P->view_x.p;
   a.marker_x = P->marker_x.p;
   a.ext_x = P->ext_x.p;
@@ -515,15 +545,26 @@ static void do_linearize(P_t* P) {
         ak.n_chunks = c1 - c0;
         ak.partials = P->part_e.p + (size_t)c0 * part;
         launch_assemble(P->rig, true, P->elim_view, ak, P->stream);
-        P->launch_count += 1;
+        // ... and so does its F pass: the piece scattered itself into f_pix, and no F chunk straddles pieces
+        AssembleArgs af = a;
+        af.oth = P->f_oth.p;
+        af.pix = P->f_pix.p;
+        af.chunks = P->f_chunks.p;
+        af.chunk_list = P->f_piece_list.p + P->f_piece_ptr[k];
+        af.n_chunks = P->f_piece_ptr[k + 1] - P->f_piece_ptr[k];
+        af.partials = P->part_f.p;
+        af.W = nullptr;
+        launch_assemble(P->rig, false, !P->elim_view, af, P->stream);
+        P->launch_count += 2;
       }
       P->launch_count -= 1;   // Scoped already counted one E-pass launch
+      f_done = true;
     } else {
       launch_assemble(P->rig, true, P->elim_view, a, P->stream);
     }
   }
   ensure_pixels(P);
-  {
+  if (!f_done) {
     Scoped t(P, ST_ASSEMBLE_F, 1);
     a.oth = P->f_oth.p;
     a.pix = P->f_pix.p;

@@ -78,6 +78,8 @@ struct rcc_ba_problem {
   rcc::DBuf<int16_t> pix_i16;        // device staging of rcc_ba_update_pixels_i16
   rcc::DBuf<rcc::Chunk> e_chunks, f_chunks;
   rcc::DBuf<int32_t> cam_chunks_e, cam_ptr_e, cam_chunks_f, cam_ptr_f;
+  rcc::DBuf<int32_t> f_piece_list;   // F-pass chunk ids grouped by upload piece
+  int f_piece_ptr[PIX_PIECES + 1] = {0};
   rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, row_pos0, col_ptr, col_pair, tile_ptr, syrk_ctas, e_count;
   rcc::DBuf<uint8_t> e_const;
 
