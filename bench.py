@@ -18,7 +18,9 @@ e2e       = same metric through the C ABI with HOST buffers: per step H2D of the
             batch (int16, rcc_ba_update_pixels_i16) + all parameter blocks, linearize, D2H of cost + gradient.
 lm_iter   = seconds per full LM iteration (linearize + Schur + reduction over ranks + Cholesky solve +
             back-substitution + candidate cost), max over ranks -- the strong-scaling curve.
-multi_gpu_parity (N>1) = N-rank vs 1-rank reduced system S, b and LM step on a small scene, run in this process.
+multi_gpu_parity (N>1) = N-rank vs 1-rank reduced system S, b and LM step on a small scene, run in this process;
+            lm_iter.step_check = cost, model decrease, step norm and candidate cost of one LM step of the benchmarked
+            problem: the problem is the same for every N, so these numbers must be too.
 """
 from __future__ import annotations
 
@@ -400,6 +402,13 @@ def measure(torch, dist, gp, scene, stream, args, rank, world, local, full=True)
     r["lm_ms"] = a.elapsed_time(b) / lm_n
     r["lm_prof"] = {k: v[0] / lm_n for k, v in gp.profile().items() if v[0] > 0}
     gp.profile_enable(False)
+    # the same LM step once more, untimed, for its numbers: the problem is fixed, so cost, model decrease, step norm
+    # and candidate cost must come out the same for every N (an end-to-end N-rank check at full size)
+    c_local = gp.linearize(want_cost=True)
+    gp.schur(1e4)
+    mcc, step_norm, x_norm = gp.solve_step()
+    r["lm_check"] = {"cost_local": c_local, "model_cost_change": mcc, "step_norm": step_norm, "x_norm": x_norm,
+                     "candidate_cost": gp.candidate_cost()}
 
     # ---------------- end-to-end steps through the C ABI with host buffers --------------
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
@@ -515,6 +524,9 @@ def run_ours(args):
     h2d_all, h2d64_all, d2h_all = int(rsum(m["h2d"])), int(rsum(m["h2d64"])), int(rsum(m["d2h"]))
     n_pairs_all = int(rsum(n_pairs_local))
 
+    lm_check = dict(m["lm_check"])
+    lm_check["cost"] = rsum(lm_check.pop("cost_local"))
+    lm_check["gain_ratio"] = (lm_check["cost"] - lm_check["candidate_cost"]) / lm_check["model_cost_change"]
     parity = multi_gpu_parity(torch, dist, rank, world, local) if world > 1 else None
 
     # ---------------- the cfg2 line beside it (N = 1 only: round-1's headline configuration) ---------------
@@ -529,7 +541,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": int(m2["h2d"]), "d2h_bytes_per_step": int(m2["d2h"])},
                 "e2e_f64_pixels": {"value": o2 * args.steps / m2["e2e64_s"], "h2d_bytes_per_step": int(m2["h2d64"])},
                 "lm_iter": {"s_per_iter": m2["lm_ms"] * 1e-3, "stage_ms": m2["lm_prof"],
-                            "reduced_system_n": int(g2.dims.n_reduced)}}
+                            "reduced_system_n": int(g2.dims.n_reduced), "step_check": m2["lm_check"]}}
         g2.close()
 
     if world > 1:
@@ -607,6 +619,7 @@ def run_ours(args):
         "clocks": clocks,
         "lm_iter": {"s_per_iter": lm_ms_max * 1e-3, "obs_per_s": obs_all / (lm_ms_max * 1e-3),
                     "stage_ms_rank0": m["lm_prof"], "reduced_system_n": n_red, "n_pairs": n_pairs_all,
+                    "step_check": lm_check,
                     "what": "linearize + Schur + reduction over ranks + reduced solve + back-substitution + candidate "
                             "cost of the whole fixed problem; the strong-scaling curve is s_per_iter over N"},
         "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[0] > 0},

@@ -546,6 +546,11 @@ static void do_linearize(P_t* P) {
         ak.partials = P->part_e.p + (size_t)c0 * part;
         launch_assemble(P->rig, true, P->elim_view, ak, P->stream);
         // ... and so does its F pass: the piece scattered itself into f_pix, and no F chunk straddles pieces
+        // (large uploads only: on cfg2-sized problems four more launches cost more than they hide)
+        if (P->n_obs < 4000000) {
+          P->launch_count += 1;
+          continue;
+        }
         AssembleArgs af = a;
         af.oth = P->f_oth.p;
         af.pix = P->f_pix.p;
@@ -558,7 +563,7 @@ static void do_linearize(P_t* P) {
         P->launch_count += 2;
       }
       P->launch_count -= 1;   // Scoped already counted one E-pass launch
-      f_done = true;
+      f_done = P->n_obs >= 4000000;
     } else {
       launch_assemble(P->rig, true, P->elim_view, a, P->stream);
     }
