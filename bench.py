@@ -361,7 +361,8 @@ def measure(torch, dist, gp, scene, stream, args, rank, world, local, full=True)
         b.record(stream)
         pairs.append((a, b))
     barrier()
-    r["launches"] = gp.launch_count() - l0 - steps       # minus the flush kernels
+    r["launches"] = gp.launch_count() - l0               # E pass + F pass + finalize per step (the untimed L2 flush
+                                                         # between steps is not counted by rcc_ba_launch_count)
     r["total_ms"] = float(sum(a.elapsed_time(b) for a, b in pairs))
     r["prof"] = gp.profile()
     gp.profile_enable(False)

@@ -73,3 +73,20 @@ def test_solve_refines_the_callers_arrays_in_place():
     assert np.abs(np.stack(views) - s.truth["views"]).max() < 1e-6
     assert np.abs(np.stack(markers) - s.truth["markers"]).max() < 1e-6
     assert np.abs(dist - s.truth["dist"][0]).max() < 1e-6
+
+
+def test_one_parameter_block_cannot_belong_to_two_gpu_cameras():
+    """A Ceres parameter block is one array: an intrinsics array shared by residual blocks whose distortion arrays
+    differ would become two independently optimised GPU cameras -- rejected instead of silently diverging; so is
+    a mix of rig and single-camera cost functions.  (Raised before any GPU object is created.)"""
+    s = make_scene(5, 6, 0.9, seed=3)
+    intr, dist_a, dist_b = s.intr[0].copy(), s.dist[0].copy(), s.dist[0].copy()
+    views = [v.copy() for v in s.views]
+    markers = [m.copy() for m in s.markers]
+    problem = Problem()
+    for b in range(s.n_blocks):
+        cost = TagReprojectionCost(s.pixels[b], s.sizes[s.marker_idx[b]])
+        problem.AddResidualBlock(cost, None, intr, dist_a if b % 2 else dist_b, views[s.view_idx[b]],
+                                 markers[s.marker_idx[b]])
+    with pytest.raises(NotImplementedError):
+        problem._build()

@@ -110,3 +110,22 @@ def test_optimise_directory_is_milestone_3(tmp_path):
     assert summ["final_cost"] < 0.2 * summ["initial_cost"]
     # integer-truncated pixels limit the accuracy; the refined map must still be closer to truth
     assert np.abs(after.markers - s.truth["markers"]).mean() < np.abs(before.markers - s.truth["markers"]).mean()
+
+
+def test_missing_intrinsics_or_targets_are_errors_and_integer_corners_stay_integers(tmp_path):
+    """A dataset without camera.yaml must not be optimised from made-up intrinsics (the reference logs
+    ROS_ERROR, camera_pose.cpp:66-67); an empty targets.yaml has no world frame; the reference's integer corners
+    (corner_detections.cpp:53-54) are read back as int16 so that they cross PCIe at 16 bytes per tag."""
+    s = make_scene(6, 5, 0.9, seed=91, round_pixels=True)
+    io_yaml.write_dataset(str(tmp_path), s)
+    r, _, _ = io_yaml.read_dataset(str(tmp_path))
+    assert r.pixels.dtype == np.int16 and np.array_equal(r.pixels, np.trunc(s.pixels).astype(np.int16))
+    os.remove(os.path.join(str(tmp_path), "camera.yaml"))
+    with pytest.raises(FileNotFoundError):
+        io_yaml.read_dataset(str(tmp_path))
+    r2, _, _ = io_yaml.read_dataset(str(tmp_path), intr=s.intr[0], dist=s.dist[0])      # explicit intrinsics are fine
+    assert np.array_equal(r2.intr[0], s.intr[0])
+    with open(os.path.join(str(tmp_path), "targets.yaml"), "w") as f:
+        f.write("targets:\n")
+    with pytest.raises(ValueError):
+        io_yaml.read_dataset(str(tmp_path), intr=s.intr[0], dist=s.dist[0])
