@@ -228,6 +228,9 @@ int rcc_ba_flush_l2(rcc_ba_problem* p);
  * extra_rows must be 0).  info: 0 or 1 + the first column with a non-positive pivot; ms: device time. */
 int rcc_dense_potrf(int32_t device, double* dA, int32_t n, int32_t ld, int32_t extra_rows, int32_t use_cusolver,
                     int32_t* info, double* ms);
+/* The back-substitution of the reduced solve on its own: L^T x = r in place (dx holds r on entry, x on return), L as
+ * left by rcc_dense_potrf.  use_cublas != 0 runs cublasDtrsv instead (the comparator). */
+int rcc_dense_trsv(int32_t device, const double* dA, int32_t n, int32_t ld, double* dx, int32_t use_cublas, double* ms);
 /* FP64 FMA microbenchmark for the roofline denominator: returns TFLOP/s */
 int rcc_fp64_peak_tflops(int32_t device, double* tflops);
 

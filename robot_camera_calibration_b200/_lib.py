@@ -102,6 +102,7 @@ SIGNATURES = {
     "rcc_ba_flush_l2": (C.c_int, [_H]),
     "rcc_dense_potrf": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int32_p,
                                   c_double_p]),
+    "rcc_dense_trsv": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, c_double_p]),
     "rcc_fp64_peak_tflops": (C.c_int, [C.c_int32, c_double_p]),
     "rcc_pnp_batch": (C.c_int, [C.c_int32, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                 C.c_int32]),

@@ -416,6 +416,126 @@ __global__ void __launch_bounds__(256, 2) chol_update_kernel(const UpdateArgs a)
 
 SmemOptIn g_diag_optin, g_panel_optin, g_update_optin;
 
+// ---------------------------------------------------------------------------------------------------------
+// K5d: back-substitution  L^T x = r  (r in x on entry), the last step of the reduced solve.
+//
+// Row i of the row-major buffer is row i of U = L^T, contiguous in j: x_i = (r_i - sum_{j>i} U(i,j) x_j) / U(i,i).
+// One CTA per 128-row block, bottom block first (blockIdx 0): it streams its rows against the 128-wide chunks of x
+// that the CTAs below it publish (flag per block, release / acquire at gpu scope; a CTA only ever waits for CTAs
+// with a smaller blockIdx, which were dispatched before it, so the wait cannot deadlock), starting the loads of a
+// chunk's tile BEFORE it waits for the chunk, then solves its own 128 x 128 triangle in four 32-row sub-steps with
+// the pre-inverted 32 x 32 diagonal blocks (trsv_inv32_kernel) and publishes its part of x.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TS_B = 128;        // rows per CTA = columns per chunk of x
+constexpr int TS_WARPS = 16;     // 8 rows per warp
+
+// inverse of every 32 x 32 diagonal block of L: one warp per block, lane = column (same recurrence as warp_potrf32)
+__global__ void __launch_bounds__(128) trsv_inv32_kernel(const double* __restrict__ A, int ld, int n,
+                                                        double* __restrict__ invd) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int b0 = b * SB;
+  if (b0 >= n) return;
+  const int w = min(SB, n - b0);                      // the last block may be narrower: padded with the identity
+  auto L = [&](int r, int c) -> double {              // L(b0 + r, b0 + c), r >= c
+    if (r < w && c < w) return A[(size_t)(b0 + c) * ld + b0 + r];
+    return r == c ? 1.0 : 0.0;
+  };
+  const double rdiag = 1.0 / L(lane, lane);
+  double m[SB];
+#pragma unroll
+  for (int i = 0; i < SB; ++i) {
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+    for (int p = 0; p < i; ++p) {
+      const double l = L(i, p);                        // uniform address across the warp
+      if (p & 1) s1 = fma(-l, m[p], s1);
+      else s0 = fma(-l, m[p], s0);
+    }
+    m[i] = (s0 + s1) * __shfl_sync(0xffffffffu, rdiag, i);
+  }
+#pragma unroll
+  for (int i = 0; i < SB; ++i) invd[(size_t)b * SB * SB + lane * SB + i] = m[i];   // inv(n = i, k = lane) at [k * 32 + n]
+}
+
+__global__ void __launch_bounds__(TS_WARPS * 32, 1) chol_trsv_kernel(const double* __restrict__ A, int ld, int n,
+                                                                     const double* __restrict__ invd, double* x,
+                                                                     int* flags, int* err) {
+  __shared__ double rs[TS_B], xs[TS_B], ts[SB];
+  const int nblk = (n + TS_B - 1) / TS_B;
+  const int blk = nblk - 1 - (int)blockIdx.x;         // bottom block first
+  const int r0 = blk * TS_B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int c = nblk - 1; c > blk; --c) {
+    const int c0 = c * TS_B + 4 * lane;
+    // tile rows of this warp against chunk c: issued before the chunk is waited for
+    double2 t0[8], t1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = r0 + 8 * warp + i;              // row < r0 + 128 <= c * 128 <= n - 1: always a real row
+      const double* p = A + (size_t)row * ld + c0;
+      t0[i] = (c0 < n) ? *reinterpret_cast<const double2*>(p) : make_double2(0.0, 0.0);
+      t1[i] = (c0 + 2 < n) ? *reinterpret_cast<const double2*>(p + 2) : make_double2(0.0, 0.0);
+      if (c0 + 1 >= n) t0[i].y = 0.0;                 // columns >= n of the buffer are not part of U
+      if (c0 + 3 >= n) t1[i].y = 0.0;
+    }
+    if (lane == 0) {
+      int spins = 0;
+      int f;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(flags + c) : "memory");
+        if (!f && ++spins > (1 << 26)) { atomicExch(err, 1); break; }    // never hang the device on a lost flag
+      } while (!f);
+    }
+    __syncwarp();
+    double xv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xv[q] = (c0 + q < n) ? __ldcg(x + c0 + q) : 0.0;     // written by another SM: L2 only
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      acc[i] = fma(t0[i].x, xv[0], fma(t0[i].y, xv[1], fma(t1[i].x, xv[2], fma(t1[i].y, xv[3], acc[i]))));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    const int row = r0 + 8 * warp + i;
+    if (lane == 0) rs[8 * warp + i] = (row < n) ? x[row] - acc[i] : 0.0;
+  }
+  __syncthreads();
+  // own triangle, bottom sub-block first
+  for (int s = TS_B / SB - 1; s >= 0; --s) {
+    const int s0 = r0 + s * SB;
+    if (s0 >= n) continue;                             // block-uniform
+    // t_i = rs_i - sum over the later sub-blocks of this block: warps 0..3 take 8 rows each, lanes the columns
+    if (warp < 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int li = s * SB + 8 * warp + i, row = r0 + li;
+        double v = 0.0;
+        if (row < n)
+          for (int j = (s + 1) * SB + lane; j < TS_B && r0 + j < n; j += 32) v = fma(A[(size_t)row * ld + r0 + j], xs[j], v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) ts[8 * warp + i] = rs[li] - v;
+      }
+    }
+    __syncthreads();
+    // x_i = sum_{k >= i} inv(L_ss)(k, i) t_k
+    if (warp == 0) {
+      const double* inv = invd + (size_t)(s0 / SB) * SB * SB + lane * SB;      // inv(k, lane) at [lane * 32 + k]
+      double v = 0.0;
+      for (int k = lane; k < SB; ++k) v = fma(inv[k], ts[k], v);
+      xs[s * SB + lane] = v;
+    }
+    __syncthreads();
+  }
+  if (tid < TS_B && r0 + tid < n) x[r0 + tid] = xs[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + blk), "r"(1) : "memory");
+}
+
 }  // namespace
 
 size_t chol_workspace_doubles() { return (size_t)NB * NB + 4 * SB * SB; }
@@ -433,6 +553,18 @@ void chol_panel(double* A, int ld, int n_rows, int k0, int kb, const double* ws,
   const size_t smem = (size_t)(NB * XST + 10 * SB * IST) * sizeof(double);
   g_panel_optin.ensure(chol_panel_kernel, smem);
   chol_panel_kernel<<<ceil_div(n_rows - (row0 & ~1), 64), 128, smem, s>>>(A, ld, n_rows, k0, kb, row0, ws, ws + NB * NB);
+  RCC_CUDA(cudaGetLastError());
+}
+
+size_t chol_trsv_workspace_doubles(int n) { return (size_t)((n + SB - 1) / SB) * SB * SB; }
+int chol_trsv_flags(int n) { return (n + TS_B - 1) / TS_B + 1; }   // + 1: the error flag
+
+void chol_trsv(const double* A, int ld, int n, double* x, double* invd, int* flags, cudaStream_t s) {
+  const int nblk = (n + TS_B - 1) / TS_B;
+  RCC_CUDA(cudaMemsetAsync(flags, 0, (size_t)(nblk + 1) * sizeof(int), s));
+  trsv_inv32_kernel<<<ceil_div((int64_t)((n + SB - 1) / SB) * 32, 128), 128, 0, s>>>(A, ld, n, invd);
+  RCC_CUDA(cudaGetLastError());
+  chol_trsv_kernel<<<nblk, TS_WARPS * 32, 0, s>>>(A, ld, n, invd, x, flags, flags + nblk);
   RCC_CUDA(cudaGetLastError());
 }
 

@@ -23,6 +23,13 @@ void chol_panel(double* A, int ld, int n_rows, int k0, int kb, const double* ws,
 void chol_update(double* A, int ld, int n_rows, int n_cols, int k0, int kb, int first_blk, int blk_stride, int n_blks,
                  cudaStream_t s);
 
+// back-substitution L^T x = r in place (x holds r on entry).  invd: chol_trsv_workspace_doubles(n) doubles (the
+// inverses of the 32 x 32 diagonal blocks, recomputed here from whatever factor is in A); flags: chol_trsv_flags(n)
+// ints, the last one is set if a wait for another CTA's part of x gave up (never expected).
+size_t chol_trsv_workspace_doubles(int n);
+int chol_trsv_flags(int n);
+void chol_trsv(const double* A, int ld, int n, double* x, double* invd, int* flags, cudaStream_t s);
+
 // per-handle resources of the panel pipeline
 struct CholDriver {
   cudaStream_t panel_stream = nullptr;   // high priority: diagonal block, panel rows, panel broadcast

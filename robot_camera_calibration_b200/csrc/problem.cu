@@ -745,8 +745,19 @@ static void do_step(P_t* P) {
     }
     extract_rhs_kernel<<<ceil_div(n, 256), 256, 0, P->stream>>>(P->S.p, n, P->ld, P->rhs.p);
     RCC_CUDA(cudaGetLastError());
-    RCC_BLAS(cublasDtrsv(P->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n, P->S.p, P->ld,
-                         P->rhs.p, 1));
+    static const bool own_trsv = !(getenv("RCC_TRSV") && std::string(getenv("RCC_TRSV")) == "cublas");
+    if (own_trsv) {
+      // hand-written back-substitution (dense.cu K5d); cublasDtrsv stays as the comparator (RCC_TRSV=cublas)
+      P->trsv_inv.ensure(chol_trsv_workspace_doubles(n));
+      P->trsv_flags.ensure((size_t)chol_trsv_flags(n));
+      chol_trsv(P->S.p, P->ld, n, P->rhs.p, P->trsv_inv.p, P->trsv_flags.p, P->stream);
+      RCC_CUDA(cudaMemcpyAsync(P->dev_info.p + 1, P->trsv_flags.p + chol_trsv_flags(n) - 1, sizeof(int),
+                               cudaMemcpyDeviceToDevice, P->stream));
+      P->launch_count += 2;
+    } else {
+      RCC_BLAS(cublasDtrsv(P->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n, P->S.p, P->ld,
+                           P->rhs.p, 1));
+    }
   }
   {
     Scoped t(P, ST_BACKSUB, 8);
@@ -840,7 +851,7 @@ static StepScalars read_step_scalars(P_t* P) {
   s.cand_cost = 0.5 * h[SX_CAND2];
   s.cur_cost = 0.5 * h[SX_COST2];
   s.gmax = std::max(h[SX_GMAX_E], h[SX_GMAX_F]);
-  s.potrf_info = hi[0];
+  s.potrf_info = hi[0] != 0 ? hi[0] : (hi[1] != 0 ? -1 : 0);   // hi[1]: the back-substitution gave up waiting (never expected)
   s.fail_lin = hi[2];
   s.fail = hi[3];
   return s;
@@ -1694,6 +1705,52 @@ int rcc_dense_potrf(int32_t device, double* dA, int32_t n, int32_t ld, int32_t e
   if (h) cusolverDnDestroy(h);
   if (work) cudaFree(work);
   if (dinfo) cudaFree(dinfo);
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
+  if (s) cudaStreamDestroy(s);
+  return rc;
+}
+
+int rcc_dense_trsv(int32_t device, const double* dA, int32_t n, int32_t ld, double* dx, int32_t use_cublas, double* ms) {
+  if (!dA || !dx || n <= 0 || ld < n) return RCC_BAD_ARG;
+  cudaStream_t s = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  cublasHandle_t h = nullptr;
+  DBuf<double> inv;
+  DBuf<int> flags;
+  int rc = RCC_OK;
+  try {
+    RCC_CUDA(cudaSetDevice(device));
+    RCC_CUDA(cudaDeviceSynchronize());
+    RCC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    RCC_CUDA(cudaEventCreate(&a));
+    RCC_CUDA(cudaEventCreate(&b));
+    if (use_cublas) {
+      RCC_BLAS(cublasCreate(&h));
+      RCC_BLAS(cublasSetStream(h, s));
+    } else {
+      inv.alloc(chol_trsv_workspace_doubles(n));
+      flags.alloc((size_t)chol_trsv_flags(n));
+    }
+    RCC_CUDA(cudaEventRecord(a, s));
+    if (use_cublas) RCC_BLAS(cublasDtrsv(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, n, dA, ld, dx, 1));
+    else chol_trsv(dA, ld, n, dx, inv.p, flags.p, s);
+    RCC_CUDA(cudaEventRecord(b, s));
+    RCC_CUDA(cudaStreamSynchronize(s));
+    float t = 0.f;
+    RCC_CUDA(cudaEventElapsedTime(&t, a, b));
+    if (ms) *ms = t;
+    if (!use_cublas) {
+      int e = 0;
+      RCC_CUDA(cudaMemcpy(&e, flags.p + chol_trsv_flags(n) - 1, sizeof(int), cudaMemcpyDeviceToHost));
+      if (e) throw Error(RCC_SOLVER_ERROR, "back-substitution: a wait for another block's part of x gave up");
+    }
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    fprintf(stderr, "[rcc_dense_trsv] %s\n", e.what());
+    rc = e.status;
+  }
+  if (h) cublasDestroy(h);
   if (a) cudaEventDestroy(a);
   if (b) cudaEventDestroy(b);
   if (s) cudaStreamDestroy(s);

@@ -102,6 +102,8 @@ struct rcc_ba_problem {
   // reduced solve: 0 = cusolverDnDpotrf replicated on every rank, 1 = dense.cu on this rank, 2 = dense.cu with the
   // block columns distributed over the ranks (RCC_CHOLESKY = cusolver | own | dist | auto)
   int chol_mode = -1;                    // -1: not resolved yet
+  rcc::DBuf<double> trsv_inv;            // K5d: inverses of the 32 x 32 diagonal blocks of the factor
+  rcc::DBuf<int> trsv_flags;
   rcc::CholDriver chol;
 
   ncclComm_t comm = nullptr;

@@ -9,7 +9,7 @@ from robot_camera_calibration_b200.scenes import config_scene
 
 cfg = int(sys.argv[1]); scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 lm_iters = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-t0 = time.time(); s = config_scene(cfg, scale=scale); t_gen = time.time() - t0
+t0 = time.time(); s = config_scene(cfg, scale=scale, blocked=True); t_gen = time.time() - t0
 t0 = time.time(); gp = BAProblem.from_scene(s); t_setup = time.time() - t0
 d = gp.dims
 for _ in range(2):
