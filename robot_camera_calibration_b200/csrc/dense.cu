@@ -457,14 +457,36 @@ __global__ void __launch_bounds__(128) trsv_inv32_kernel(const double* __restric
   for (int i = 0; i < SB; ++i) invd[(size_t)b * SB * SB + lane * SB + i] = m[i];   // inv(n = i, k = lane) at [k * 32 + n]
 }
 
+constexpr int TS_UST = TS_B + 2;     // shared-memory row stride of the diagonal tile
+constexpr int TS_IST = SB + 1;       // and of the transposed inverses (lane = column reads stay conflict-free)
+
 __global__ void __launch_bounds__(TS_WARPS * 32, 1) chol_trsv_kernel(const double* __restrict__ A, int ld, int n,
                                                                      const double* __restrict__ invd, double* x,
                                                                      int* flags, int* err) {
-  __shared__ double rs[TS_B], xs[TS_B], ts[SB];
+  extern __shared__ __align__(16) double sm[];
+  double* Us = sm;                              // [128][TS_UST]  U(r0 + i, r0 + j): the block's own triangle
+  double* Is = Us + TS_B * TS_UST;              // [4][32][TS_IST] inv(L_ss)(k, i) at [s][k * TS_IST + i]
+  double* rs = Is + 4 * SB * TS_IST;            // [128]
+  double* xs = rs + TS_B;                       // [128]
+  double* ts = xs + TS_B;                       // [32]
   const int nblk = (n + TS_B - 1) / TS_B;
   const int blk = nblk - 1 - (int)blockIdx.x;         // bottom block first
   const int r0 = blk * TS_B;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the block's own triangle and its four inverted diagonal blocks go to shared memory now (asynchronously): the
+  // final sub-steps are on the critical path of every block above this one and must not wait for global memory
+  for (int idx = tid; idx < TS_B * (TS_B / 2); idx += TS_WARPS * 32) {
+    const int i = idx >> 6, j2 = (idx & 63) * 2;
+    const bool ok = r0 + i < n && r0 + j2 < n;
+    cp_async16(Us + i * TS_UST + j2, ok ? A + (size_t)(r0 + i) * ld + r0 + j2 : A, ok ? 16 : 0);
+  }
+  cp_async_commit();
+  for (int idx = tid; idx < 4 * SB * SB; idx += TS_WARPS * 32) {
+    const int s = idx >> 10, i = (idx >> 5) & 31, k = idx & 31;        // invd: inv(k, i) at [i * 32 + k]
+    const int b32 = r0 / SB + s;
+    Is[s * SB * TS_IST + k * TS_IST + i] = (b32 * SB < n) ? invd[(size_t)b32 * SB * SB + i * SB + k] : 0.0;
+  }
+  if (tid < TS_B) xs[tid] = 0.0;                      // entries past the end of the matrix stay zero
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int c = nblk - 1; c > blk; --c) {
     const int c0 = c * TS_B + 4 * lane;
@@ -502,19 +524,22 @@ __global__ void __launch_bounds__(TS_WARPS * 32, 1) chol_trsv_kernel(const doubl
     const int row = r0 + 8 * warp + i;
     if (lane == 0) rs[8 * warp + i] = (row < n) ? x[row] - acc[i] : 0.0;
   }
+  cp_async_wait<0>();
   __syncthreads();
-  // own triangle, bottom sub-block first
+  // own triangle, bottom sub-block first, everything from shared memory
   for (int s = TS_B / SB - 1; s >= 0; --s) {
-    const int s0 = r0 + s * SB;
-    if (s0 >= n) continue;                             // block-uniform
+    if (r0 + s * SB >= n) continue;                    // block-uniform
     // t_i = rs_i - sum over the later sub-blocks of this block: warps 0..3 take 8 rows each, lanes the columns
     if (warp < 4) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int li = s * SB + 8 * warp + i, row = r0 + li;
+        const int li = s * SB + 8 * warp + i;
         double v = 0.0;
-        if (row < n)
-          for (int j = (s + 1) * SB + lane; j < TS_B && r0 + j < n; j += 32) v = fma(A[(size_t)row * ld + r0 + j], xs[j], v);
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+          const int j = (s + 1) * SB + lane + 32 * jj;
+          if (j < TS_B) v = fma(Us[li * TS_UST + j], xs[j], v);      // xs of sub-blocks not yet solved is never read:
+        }                                                           // j >= (s+1)*32 were solved in earlier sub-steps
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) ts[8 * warp + i] = rs[li] - v;
@@ -523,10 +548,14 @@ __global__ void __launch_bounds__(TS_WARPS * 32, 1) chol_trsv_kernel(const doubl
     __syncthreads();
     // x_i = sum_{k >= i} inv(L_ss)(k, i) t_k
     if (warp == 0) {
-      const double* inv = invd + (size_t)(s0 / SB) * SB * SB + lane * SB;      // inv(k, lane) at [lane * 32 + k]
-      double v = 0.0;
-      for (int k = lane; k < SB; ++k) v = fma(inv[k], ts[k], v);
-      xs[s * SB + lane] = v;
+      const double* inv = Is + s * SB * TS_IST + lane;
+      double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < SB; k += 2) {               // inv(k, i) = 0 for k < i: no branch needed
+        v0 = fma(inv[k * TS_IST], ts[k], v0);
+        v1 = fma(inv[(k + 1) * TS_IST], ts[k + 1], v1);
+      }
+      xs[s * SB + lane] = v0 + v1;
     }
     __syncthreads();
   }
@@ -535,6 +564,8 @@ __global__ void __launch_bounds__(TS_WARPS * 32, 1) chol_trsv_kernel(const doubl
   __syncthreads();
   if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + blk), "r"(1) : "memory");
 }
+
+SmemOptIn g_trsv_optin;
 
 }  // namespace
 
@@ -564,7 +595,9 @@ void chol_trsv(const double* A, int ld, int n, double* x, double* invd, int* fla
   RCC_CUDA(cudaMemsetAsync(flags, 0, (size_t)(nblk + 1) * sizeof(int), s));
   trsv_inv32_kernel<<<ceil_div((int64_t)((n + SB - 1) / SB) * 32, 128), 128, 0, s>>>(A, ld, n, invd);
   RCC_CUDA(cudaGetLastError());
-  chol_trsv_kernel<<<nblk, TS_WARPS * 32, 0, s>>>(A, ld, n, invd, x, flags, flags + nblk);
+  const size_t smem = (size_t)(TS_B * TS_UST + 4 * SB * TS_IST + 2 * TS_B + SB) * sizeof(double);
+  g_trsv_optin.ensure(chol_trsv_kernel, smem);
+  chol_trsv_kernel<<<nblk, TS_WARPS * 32, smem, s>>>(A, ld, n, invd, x, flags, flags + nblk);
   RCC_CUDA(cudaGetLastError());
 }
 
