@@ -429,29 +429,34 @@ SmemOptIn g_diag_optin, g_panel_optin, g_update_optin;
 constexpr int TS_B = 128;        // rows per CTA = columns per chunk of x
 constexpr int TS_WARPS = 16;     // 8 rows per warp
 
-// inverse of every 32 x 32 diagonal block of L: one warp per block, lane = column (same recurrence as warp_potrf32)
+// inverse of every 32 x 32 diagonal block of L: one warp per block; the block is staged in shared memory (32 coalesced
+// column loads in flight at once), then lane = column runs the same recurrence as warp_potrf32
 __global__ void __launch_bounds__(128) trsv_inv32_kernel(const double* __restrict__ A, int ld, int n,
                                                         double* __restrict__ invd) {
+  __shared__ double blk_all[4][SB * IST];
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int b0 = b * SB;
-  if (b0 >= n) return;
-  const int w = min(SB, n - b0);                      // the last block may be narrower: padded with the identity
-  auto L = [&](int r, int c) -> double {              // L(b0 + r, b0 + c), r >= c
-    if (r < w && c < w) return A[(size_t)(b0 + c) * ld + b0 + r];
-    return r == c ? 1.0 : 0.0;
-  };
-  const double rdiag = 1.0 / L(lane, lane);
+  if (b0 >= n) return;                                 // whole warps leave together
+  double* blk = blk_all[threadIdx.x >> 5];             // L(b0 + r, b0 + c) at blk[c * IST + r]
+  const int w = min(SB, n - b0);                       // the last block may be narrower: padded with the identity
+#pragma unroll
+  for (int c = 0; c < SB; ++c)
+    blk[c * IST + lane] = (lane < w && c < w) ? A[(size_t)(b0 + c) * ld + b0 + lane] : (lane == c ? 1.0 : 0.0);
+  __syncwarp();
+  const double rdiag = 1.0 / blk[lane * IST + lane];
   double m[SB];
 #pragma unroll
   for (int i = 0; i < SB; ++i) {
-    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int p = 0; p < i; ++p) {
-      const double l = L(i, p);                        // uniform address across the warp
-      if (p & 1) s1 = fma(-l, m[p], s1);
-      else s0 = fma(-l, m[p], s0);
+      const double l = blk[p * IST + i];               // uniform address across the warp: broadcast
+      if ((p & 3) == 0) s0 = fma(-l, m[p], s0);
+      else if ((p & 3) == 1) s1 = fma(-l, m[p], s1);
+      else if ((p & 3) == 2) s2 = fma(-l, m[p], s2);
+      else s3 = fma(-l, m[p], s3);
     }
-    m[i] = (s0 + s1) * __shfl_sync(0xffffffffu, rdiag, i);
+    m[i] = ((s0 + s1) + (s2 + s3)) * __shfl_sync(0xffffffffu, rdiag, i);
   }
 #pragma unroll
   for (int i = 0; i < SB; ++i) invd[(size_t)b * SB * SB + lane * SB + i] = m[i];   // inv(n = i, k = lane) at [k * 32 + n]

@@ -32,6 +32,21 @@ for n in sizes:
             del buf
         out[name + "_ms"] = best
         out[name + "_tflops"] = n ** 3 / 3 / best / 1e9
+        if name == "own":
+            # back-substitution on the factor just computed: hand-written kernel vs cublasDtrsv
+            buf = torch.zeros((n + 1, ld), dtype=torch.float64, device="cuda")
+            buf[:n, :n] = S
+            lib.rcc_dense_potrf(0, C.c_void_p(buf.data_ptr()), n, ld, 1, 0, C.byref(info), C.byref(C.c_double()))
+            r = torch.randn(n, dtype=torch.float64, device="cuda")
+            for tname, cub in (("trsv_own", 0), ("trsv_cublas", 1)):
+                tb = 1e30
+                for rep in range(4):
+                    x = r.clone()
+                    ms = C.c_double()
+                    assert lib.rcc_dense_trsv(0, C.c_void_p(buf.data_ptr()), n, ld, C.c_void_p(x.data_ptr()), cub, C.byref(ms)) == 0
+                    tb = min(tb, ms.value)
+                out[tname + "_ms"] = tb
+            del buf
     print(json.dumps(out), flush=True)
     del S
     if n >= 20000:
