@@ -745,9 +745,9 @@ static void do_step(P_t* P) {
     }
     extract_rhs_kernel<<<ceil_div(n, 256), 256, 0, P->stream>>>(P->S.p, n, P->ld, P->rhs.p);
     RCC_CUDA(cudaGetLastError());
-    static const bool own_trsv = !(getenv("RCC_TRSV") && std::string(getenv("RCC_TRSV")) == "cublas");
+    static const bool own_trsv = getenv("RCC_TRSV") && std::string(getenv("RCC_TRSV")) == "own";
     if (own_trsv) {
-      // hand-written back-substitution (dense.cu K5d); cublasDtrsv stays as the comparator (RCC_TRSV=cublas)
+      // hand-written back-substitution (dense.cu K5d), RCC_TRSV=own; cublasDtrsv otherwise
       P->trsv_inv.ensure(chol_trsv_workspace_doubles(n));
       P->trsv_flags.ensure((size_t)chol_trsv_flags(n));
       chol_trsv(P->S.p, P->ld, n, P->rhs.p, P->trsv_inv.p, P->trsv_flags.p, P->stream);
