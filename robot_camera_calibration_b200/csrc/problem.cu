@@ -745,9 +745,12 @@ static void do_step(P_t* P) {
     }
     extract_rhs_kernel<<<ceil_div(n, 256), 256, 0, P->stream>>>(P->S.p, n, P->ld, P->rhs.p);
     RCC_CUDA(cudaGetLastError());
-    static const bool own_trsv = getenv("RCC_TRSV") && std::string(getenv("RCC_TRSV")) == "own";
+    // hand-written back-substitution (dense.cu K5d) where it is the faster one: 0.49 / 0.98 / 2.63 ms against
+    // cublasDtrsv's 0.59 / 1.16 / 3.08 ms at n = 6 030 / 12 060 / 30 009, but 0.25 against 0.23 ms at n = 3 009 (the
+    // hand-off between the 128-row blocks costs ~10 us each).  RCC_TRSV = own | cublas overrides.
+    const char* tv = getenv("RCC_TRSV");
+    const bool own_trsv = tv ? std::string(tv) == "own" : n >= 4500;
     if (own_trsv) {
-      // hand-written back-substitution (dense.cu K5d), RCC_TRSV=own; cublasDtrsv otherwise
       P->trsv_inv.ensure(chol_trsv_workspace_doubles(n));
       P->trsv_flags.ensure((size_t)chol_trsv_flags(n));
       chol_trsv(P->S.p, P->ld, n, P->rhs.p, P->trsv_inv.p, P->trsv_flags.p, P->stream);
