@@ -42,6 +42,31 @@ for name, kw in (("single", dict(n_markers=40, n_views=120, visibility=0.5, seed
                          dintr=float(np.abs(intr - i1).max()), ddist=float(np.abs(dst - d1).max()),
                          allreduce_ms=summ["allreduce_ms"])
     dist.barrier()
+if os.environ.get("RCC_CHECK_BIG") == "1":
+    # one LM step of a rig problem whose reduced system (n = 12 060, cfg3's tags and cameras, 10 % of its body poses)
+    # is large enough for the automatic choice of the distributed Cholesky and the packed all-reduce
+    from robot_camera_calibration_b200.scenes import config_scene
+    os.environ.pop("RCC_CHOLESKY", None)
+    os.environ.pop("RCC_PACK_MIN_N", None)
+    scene = config_scene(3, scale=0.1, blocked=True)
+    dba = DistributedBA(scene, device=local, eliminate="views")
+    p = dba.problem
+    p.linearize(); p.schur(1e4); p.solve_step()
+    st = p.step()
+    cand = p.candidate_cost()
+    dba.close()
+    if rank == 0:
+        os.environ["RCC_CHOLESKY"] = "cusolver"
+        with BAProblem.from_scene(scene, device=local, eliminate="views") as gp:
+            gp.linearize(); gp.schur(1e4); gp.solve_step()
+            s1 = gp.step()
+            c1 = gp.candidate_cost()
+        dF = np.concatenate([st["d_f"].ravel(), st["d_shared"]]); d1 = np.concatenate([s1["d_f"].ravel(), s1["d_shared"]])
+        out["cfg3_one_step"] = dict(n_reduced=int(6 * len(scene.markers) + 15 * len(scene.intr)),
+                                    delta_F_rel=float(np.linalg.norm(dF - d1) / np.linalg.norm(d1)),
+                                    candidate_cost=(cand, c1), iters=(1, 1), cost=(cand, c1),
+                                    dviews=0.0, dmarkers=float(np.abs(st["d_f"] - s1["d_f"]).max()), ddist=0.0)
+    dist.barrier()
 if rank == 0:
     ok = all(v["dviews"] < 1e-8 and v["dmarkers"] < 1e-8 and v["ddist"] < 1e-8 and
              abs(v["cost"][0] - v["cost"][1]) <= 1e-10 * v["cost"][1] for v in out.values())
