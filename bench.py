@@ -250,8 +250,8 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def multi_gpu_parity(torch, dist, rank, world, local):
-    """N-rank vs 1-rank on a small scene, through the library's NCCL path: reduced system (sum of the ranks'
-    partial S, b against the 1-rank S, b), the LM step (solve_step with the communicator) and a converged solve.
+    """N-rank vs 1-rank on a small scene, through the library's NCCL path: the reduced system S, b as the library
+    leaves it on every rank after its band-wise all-reduce, the LM step (solve_step) and a converged solve.
     Relative Frobenius errors; bar 1e-9 (FP64 sums in a different order)."""
     from robot_camera_calibration_b200.dist import shard_scene
     from robot_camera_calibration_b200.problem import BAProblem
@@ -269,7 +269,7 @@ def multi_gpu_parity(torch, dist, rank, world, local):
     for name, chol, kw in cases:
         kw = dict(kw)
         os.environ["RCC_CHOLESKY"] = chol
-        os.environ["RCC_PACK_MIN_N"] = "0" if chol == "dist" else "1000000"     # packed-triangle all-reduce, like cfg4
+        os.environ["RCC_SYRK_GROUPS"] = "3" if chol == "dist" else "1"         # several reduction bands, like cfg4
         scene = make_scene(kw.pop("n_markers"), kw.pop("n_views"), kw.pop("visibility"), **kw)
         local_scene, (lo, hi) = shard_scene(scene, rank, world, "views")
         gp = BAProblem.from_scene(local_scene, device=local, eliminate="views")
@@ -277,12 +277,10 @@ def multi_gpu_parity(torch, dist, rank, world, local):
         dist.broadcast_object_list(ids, src=0)
         gp.comm_init(ids[0], rank, world)
         gp.linearize()
-        gp.schur(1e4)
-        S, b = gp.reduced_system()                       # this rank's partial sums
-        t = torch.from_numpy(np.concatenate([S.ravel(), b])).cuda()
-        dist.all_reduce(t)
-        Sb = t.cpu().numpy()
-        gp.solve_step()                                  # all-reduce + factorisation + back-substitution in the library
+        gp.schur(1e4)                                    # collective: the library sums S over the ranks behind the SYRK
+        S, b = gp.reduced_system()                       # ... so every rank holds the whole reduced system here
+        Sb = np.concatenate([S.ravel(), b])
+        gp.solve_step()                                  # factorisation (distributed or replicated) + back-substitution
         st = gp.step()
         parts = [None] * world
         dist.all_gather_object(parts, (lo, hi, st["d_e"][lo:hi], st["d_f"], st["d_shared"]))
@@ -317,7 +315,7 @@ def multi_gpu_parity(torch, dist, rank, world, local):
                          "converged_views_max_abs": float(np.abs(views_all - v1).max()),
                          "converged_markers_max_abs": float(np.abs(markers_n - m1).max())}
         dist.barrier()
-    os.environ.pop("RCC_PACK_MIN_N", None)
+    os.environ.pop("RCC_SYRK_GROUPS", None)
     if saved is None:
         os.environ.pop("RCC_CHOLESKY", None)
     else:

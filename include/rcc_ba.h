@@ -162,11 +162,13 @@ int rcc_ba_evaluate_device(rcc_ba_problem* p, int32_t want_jacobians, double* co
 /* ---- normal equations, Schur complement, LM step ------------------------- */
 /* residual + Jacobian + J^T J / J^T r blocks, fused (no Jacobian in HBM) */
 int rcc_ba_linearize(rcc_ba_problem* p, double* cost /*may be NULL: no host sync*/);
-/* damped Schur complement into the reduced system (local partial on this rank).  Uses the LM diagonal bounds and
- * the Jacobi-scaling flag of the last rcc_ba_solve / rcc_ba_set_lm_diagonal (defaults 1e-6, 1e32, no scaling). */
+/* damped Schur complement into the reduced system.  With a communicator attached (rcc_ba_comm_init) this is a
+ * COLLECTIVE call: the ranks' partial systems are summed band by band behind the computation, and the reduced system
+ * every rank holds on return is the sum over all ranks.  Uses the LM diagonal bounds and the Jacobi-scaling flag of
+ * the last rcc_ba_solve / rcc_ba_set_lm_diagonal (defaults 1e-6, 1e32, no scaling). */
 int rcc_ba_schur(rcc_ba_problem* p, double radius);
 int rcc_ba_set_lm_diagonal(rcc_ba_problem* p, double min_diagonal, double max_diagonal, int32_t jacobi_scaling);
-/* [all-reduce over ranks] + constant mask + Cholesky + back-substitution.
+/* constant mask + Cholesky (distributed over the ranks for large systems) + back-substitution.
  * model_cost_change may be NULL. */
 int rcc_ba_solve_step(rcc_ba_problem* p, double* model_cost_change, double* step_norm, double* x_norm);
 /* cost at x + step (all-reduced over ranks) */
@@ -192,7 +194,7 @@ int rcc_ba_get_dims(rcc_ba_problem* p, rcc_ba_dims* d);
  *   W    n_obs_blocks x 6 x 6 (= J_e^T J_f per block, caller's observation order) */
 int rcc_ba_get_normal_blocks(rcc_ba_problem* p, double* Hee, double* ge, double* Hes, double* Hff, double* gf,
                              double* Hfs, double* Hss, double* gs, double* W);
-/* reduced system after rcc_ba_schur (+ all-reduce/mask if rcc_ba_solve_step ran):
+/* reduced system after rcc_ba_schur (summed over the ranks when a communicator is attached):
  * S n_reduced x n_reduced row-major, both triangles filled; b n_reduced */
 int rcc_ba_get_reduced_system(rcc_ba_problem* p, double* S, double* b);
 /* a rectangular window of the same matrix without materialising it on the host (n_reduced = 30 009 is 7.2 GB):

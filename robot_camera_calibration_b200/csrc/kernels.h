@@ -270,11 +270,11 @@ void launch_f_stats(const double* gF, const double* d2f, const double* delta_F, 
 // reduce the per-E-block partials: out[0..2]
 void launch_e_stats(const double* partials, int32_t n_e, double* out3, cudaStream_t s);
 
-// all-reduce of the reduced buffer without its dead lower triangle: row j of the row-major upper triangle keeps its
-// elements [j, ld); `packed` holds the rows back to back (row j at j*ld - j(j-1)/2), then the `tail` doubles that
-// follow row n-1 in S.  to_packed = false copies back.
-size_t packed_upper_doubles(int32_t n, int32_t ld, size_t tail);
-void launch_pack_upper(double* S, int32_t n, int32_t ld, size_t tail, double* packed, bool to_packed, cudaStream_t s);
+// a column band of the reduced buffer for the overlapped reduction: rows [0, min(n_rows, c1)), columns
+// [max(row, c0), c1) of each row (the live part of the upper triangle inside the band), rows back to back in `packed`
+size_t packed_band_doubles(int32_t n_rows, int32_t c0, int32_t c1);
+void launch_pack_band(double* S, int32_t ld, int32_t n_rows, int32_t c0, int32_t c1, double* packed, bool to_packed,
+                      cudaStream_t s);
 // x_new = x + delta (6-dof blocks and shared block)
 void launch_apply(const double* x, const double* d, double* out, int64_t n, cudaStream_t s);
 // make a symmetric full matrix out of the upper triangle (parity read-back only)

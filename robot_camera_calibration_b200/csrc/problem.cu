@@ -102,6 +102,9 @@ rcc_ba_problem::~rcc_ba_problem() {
     if (hs.ev) cudaEventDestroy(hs.ev);
   }
   if (own_stream && stream) cudaStreamDestroy(stream);
+  if (comm_stream) cudaStreamDestroy(comm_stream);
+  for (auto e : ev_grp)
+    if (e) cudaEventDestroy(e);
   if (side_stream) cudaStreamDestroy(side_stream);
   if (side_stream2) cudaStreamDestroy(side_stream2);
   if (ev_fork) cudaEventDestroy(ev_fork);
@@ -456,6 +459,31 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
       cta_list[2 * i + 1] = (int32_t)(order[i] % nct);
     }
     P->n_syrk_ctas = (int)order.size();
+    {
+      // groups of column tiles with about equal CTA counts; few groups when the reduced system is small (each group
+      // is one all-reduce: below ~64 MB per group the launch latency would outweigh what the overlap hides)
+      const size_t bytes = (size_t)P->n_red * P->n_red * 4;          // upper triangle in bytes
+      int G = (int)std::min<size_t>(rcc_ba_problem::SYRK_GROUPS, std::max<size_t>(1, bytes / ((size_t)64 << 20)));
+      if (env_int("RCC_SYRK_GROUPS", 0) > 0) G = std::min((int)rcc_ba_problem::SYRK_GROUPS, env_int("RCC_SYRK_GROUPS", 0));   // tests
+      G = std::max(1, std::min(G, nct));
+      P->n_syrk_groups = G;
+      P->syrk_grp_cta[0] = 0;
+      P->syrk_grp_col[0] = 0;
+      int64_t cum = 0;
+      int g = 1;
+      for (int J = 0; J < nct && g < G; ++J) {
+        cum += std::min(P->n_f, (J + 1) * 32 * cs);
+        if (cum * G >= (int64_t)order.size() * g) {
+          P->syrk_grp_cta[g] = (int)cum;
+          P->syrk_grp_col[g] = std::min(6 * P->n_f, (J + 1) * 32 * cs * 6);
+          ++g;
+        }
+      }
+      for (; g <= rcc_ba_problem::SYRK_GROUPS; ++g) {               // the last real group ends at the end; the rest are empty
+        P->syrk_grp_cta[g] = (int)order.size();
+        P->syrk_grp_col[g] = 6 * P->n_f;
+      }
+    }
     if (cta_list.empty()) cta_list.assign(2, 0);
     P->syrk_ctas.upload(cta_list, s);
     RCC_CUDA(cudaStreamSynchronize(s));
@@ -593,6 +621,7 @@ static void do_linearize(P_t* P) {
 
 static void do_schur(P_t* P, double radius) {
   RCC_REQUIRE(P->linearized, RCC_NOT_READY, "linearize has not been called");
+  bool eager = false;
   RCC_REQUIRE(radius > 0, RCC_BAD_ARG, "radius must be positive");
   refresh_constants(P);
   P->radius_used = radius;
@@ -627,9 +656,60 @@ static void do_schur(P_t* P, double radius) {
                       P->S.p};
     launch_reduced_tail(r, P->side_stream);
     RCC_CUDA(cudaEventRecord(P->ev_join, P->side_stream));
-    launch_schur_syrk(a, P->stream);
-    RCC_CUDA(cudaStreamWaitEvent(P->stream, P->ev_join, 0));
+    eager = P->comm != nullptr && P->n_ranks > 1;
+    if (!eager) {
+      launch_schur_syrk(a, P->stream);
+      RCC_CUDA(cudaStreamWaitEvent(P->stream, P->ev_join, 0));
+    } else {
+      // Several ranks: the sum over the ranks overlaps with the SYRK.  The work list is column-tile major, so a group
+      // of column tiles = a band of columns of S is final as soon as its CTAs are done: the communication stream
+      // packs the band's live part (upper triangle inside the band), all-reduces it and unpacks it while the main
+      // stream computes the next band.  The border band (shared parameters, rhs) and the tail rows come last.
+      const int n = P->n_red;
+      const size_t tail = 2 * (size_t)n + 8;
+      size_t need = packed_band_doubles(n, 6 * P->n_f, P->ld) + tail;
+      for (int g = 0; g < P->n_syrk_groups; ++g) need += packed_band_doubles(n, P->syrk_grp_col[g], P->syrk_grp_col[g + 1]);
+      P->packed_S.ensure(need);
+      size_t off = 0;
+      for (int g = 0; g < P->n_syrk_groups; ++g) {
+        SchurSyrkArgs ag = a;
+        ag.cta_list = P->syrk_ctas.p + 2 * (size_t)P->syrk_grp_cta[g];
+        ag.n_ctas = P->syrk_grp_cta[g + 1] - P->syrk_grp_cta[g];
+        launch_schur_syrk(ag, P->stream);
+        RCC_CUDA(cudaEventRecord(P->ev_grp[g], P->stream));
+        RCC_CUDA(cudaStreamWaitEvent(P->comm_stream, P->ev_grp[g], 0));
+        const int c0 = P->syrk_grp_col[g], c1 = P->syrk_grp_col[g + 1];
+        const size_t cnt = packed_band_doubles(n, c0, c1);
+        if (cnt == 0) continue;
+        launch_pack_band(P->S.p, P->ld, n, c0, c1, P->packed_S.p + off, true, P->comm_stream);
+        RCC_NCCL(ncclAllReduce(P->packed_S.p + off, P->packed_S.p + off, cnt, ncclDouble, ncclSum, P->comm, P->comm_stream));
+        launch_pack_band(P->S.p, P->ld, n, c0, c1, P->packed_S.p + off, false, P->comm_stream);
+        off += cnt;
+        P->launch_count += 3;
+      }
+      {
+        RCC_CUDA(cudaStreamWaitEvent(P->comm_stream, P->ev_join, 0));
+        const int c0 = 6 * P->n_f, c1 = P->ld;
+        const size_t cnt = packed_band_doubles(n, c0, c1);
+        double* pk = P->packed_S.p + off;
+        launch_pack_band(P->S.p, P->ld, n, c0, c1, pk, true, P->comm_stream);
+        RCC_CUDA(cudaMemcpyAsync(pk + cnt, P->S.p + (size_t)n * P->ld, tail * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 P->comm_stream));
+        RCC_NCCL(ncclAllReduce(pk, pk, cnt + tail, ncclDouble, ncclSum, P->comm, P->comm_stream));
+        launch_pack_band(P->S.p, P->ld, n, c0, c1, pk, false, P->comm_stream);
+        RCC_CUDA(cudaMemcpyAsync(P->S.p + (size_t)n * P->ld, pk + cnt, tail * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 P->comm_stream));
+        RCC_CUDA(cudaEventRecord(P->ev_grp[rcc_ba_problem::SYRK_GROUPS], P->comm_stream));
+        P->launch_count += 2;
+      }
+    }
   }
+  if (eager) {
+    // what is left of the reduction once the last band has been computed
+    Scoped t(P, ST_ALLREDUCE, 1);
+    RCC_CUDA(cudaStreamWaitEvent(P->stream, P->ev_grp[rcc_ba_problem::SYRK_GROUPS], 0));
+  }
+  P->reduced_in_schur = eager;
   P->schur_done = true;
   P->step_ready = P->cand_ready = false;
 }
@@ -699,23 +779,8 @@ static int cholesky_mode(P_t* P) {
 static void do_step(P_t* P) {
   RCC_REQUIRE(P->schur_done, RCC_NOT_READY, "schur has not been called");
   const int n = P->n_red;
-  if (P->comm) {
-    Scoped t(P, ST_ALLREDUCE, 1);
-    const size_t tail = 2 * (size_t)n + 8;
-    if (n >= env_int("RCC_PACK_MIN_N", 6000)) {
-      // half of the square buffer is the dead lower triangle: pack the rows' live parts, reduce 3.6 GB instead of
-      // 7.2 GB (cfg4), unpack; the two copies cost ~2.5 ms of HBM time against ~8 ms of link time saved
-      const size_t count = packed_upper_doubles(n, P->ld, tail);
-      P->packed_S.ensure(count);
-      launch_pack_upper(P->S.p, n, P->ld, tail, P->packed_S.p, true, P->stream);
-      RCC_NCCL(ncclAllReduce(P->packed_S.p, P->packed_S.p, count, ncclDouble, ncclSum, P->comm, P->stream));
-      launch_pack_upper(P->S.p, n, P->ld, tail, P->packed_S.p, false, P->stream);
-      P->launch_count += 2;
-    } else {
-      const size_t count = (size_t)n * P->ld + tail;
-      RCC_NCCL(ncclAllReduce(P->S.p, P->S.p, count, ncclDouble, ncclSum, P->comm, P->stream));
-    }
-  }
+  // several ranks: rcc_ba_schur has already summed S over the ranks, band by band, behind its SYRK
+  RCC_REQUIRE(!P->comm || P->reduced_in_schur, RCC_NOT_READY, "reduced system not summed over the ranks");
   {
     Scoped t(P, ST_MASK, 3);
     MaskArgs m{n, P->ld, P->radius_used, P->min_diag, P->max_diag, P->jacobi, P->const_idx.p, P->n_const, P->S.p, P->rhs.p,
@@ -1612,6 +1677,9 @@ int rcc_ba_comm_init(rcc_ba_problem* P, const char id[RCC_COMM_ID_BYTES], int32_
     ncclUniqueId u;
     memcpy(&u, id, sizeof(u));
     RCC_NCCL(ncclCommInitRank(&P->comm, n_ranks, u, rank));
+    if (!P->comm_stream) RCC_CUDA(cudaStreamCreateWithFlags(&P->comm_stream, cudaStreamNonBlocking));
+    for (auto& e : P->ev_grp)
+      if (!e) RCC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   API_END(P)
 }

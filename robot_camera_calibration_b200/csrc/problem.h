@@ -47,6 +47,15 @@ struct rcc_ba_problem {
   int n_bb = 2, n_red = 0, ld = 0;
   int64_t n_obs = 0, n_pairs = 0;
   int tile_w = 32, n_tiles = 1, n_syrk_ctas = 0;
+  // overlapped reduction (multi-rank): the SYRK work list is cut into groups of column tiles; group g covers the
+  // CTAs [syrk_grp_cta[g], syrk_grp_cta[g+1]) and the columns [syrk_grp_col[g], syrk_grp_col[g+1]) of S
+  static constexpr int SYRK_GROUPS = 8;
+  int n_syrk_groups = 1;
+  int syrk_grp_cta[SYRK_GROUPS + 1] = {0};
+  int syrk_grp_col[SYRK_GROUPS + 1] = {0};
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_grp[SYRK_GROUPS + 1] = {nullptr};
+  bool reduced_in_schur = false;     // S already holds the sum over the ranks (rcc_ba_schur did the all-reduce)
   int n_chunks_e = 0, n_chunks_f = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -95,7 +104,7 @@ struct rcc_ba_problem {
 
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
-  rcc::DBuf<double> potrf_work, packed_S;   // packed_S: upper triangle + tail for the all-reduce (multi-rank, large n)
+  rcc::DBuf<double> potrf_work, packed_S;   // packed_S: the packed column bands of the overlapped reduction (multi-rank)
   rcc::DBuf<int> dev_info;
   int potrf_lwork = 0;
 

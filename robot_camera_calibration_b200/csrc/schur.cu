@@ -775,30 +775,31 @@ void launch_apply(const double* x, const double* d, double* out, int64_t n, cuda
   RCC_CUDA(cudaGetLastError());
 }
 
-size_t packed_upper_doubles(int32_t n, int32_t ld, size_t tail) {
-  return (size_t)n * ld - (size_t)n * (n - 1) / 2 + tail;
+// ---- column bands (overlapped reduction): row i < c0 keeps [c0, c1), row i in [c0, c1) keeps [i, c1)
+static __host__ __device__ inline size_t band_row_offset(int64_t i, int64_t c0, int64_t c1) {
+  const int64_t w = c1 - c0;
+  if (i <= c0) return (size_t)(i * w);
+  const int64_t t = i - c0;                     // rows c0 .. i-1 of the triangle: sum_{k=0}^{t-1} (w - k)
+  return (size_t)(c0 * w + t * w - t * (t - 1) / 2);
 }
-// one CTA per row (the last CTA takes the tail); rows are contiguous on both sides
-__global__ void __launch_bounds__(256) pack_upper_kernel(double* __restrict__ S, int n, int ld, size_t tail,
-                                                         double* __restrict__ packed, bool to_packed) {
-  const int j = blockIdx.x;
-  double* a;
-  double* b;
-  size_t len;
-  if (j < n) {
-    a = S + (size_t)j * ld + j;
-    b = packed + ((size_t)j * ld - (size_t)j * (j - 1) / 2);
-    len = (size_t)(ld - j);
-  } else {
-    a = S + (size_t)n * ld;
-    b = packed + ((size_t)n * ld - (size_t)n * (n - 1) / 2);
-    len = tail;
-  }
-  if (to_packed) for (size_t i = threadIdx.x; i < len; i += 256) b[i] = a[i];
-  else for (size_t i = threadIdx.x; i < len; i += 256) a[i] = b[i];
+size_t packed_band_doubles(int32_t n_rows, int32_t c0, int32_t c1) {
+  return band_row_offset(std::min<int64_t>(n_rows, c1), c0, c1);
 }
-void launch_pack_upper(double* S, int32_t n, int32_t ld, size_t tail, double* packed, bool to_packed, cudaStream_t s) {
-  pack_upper_kernel<<<n + 1, 256, 0, s>>>(S, n, ld, tail, packed, to_packed);
+__global__ void __launch_bounds__(256) pack_band_kernel(double* __restrict__ S, int ld, int c0, int c1,
+                                                        double* __restrict__ packed, bool to_packed) {
+  const int i = blockIdx.x;
+  const int start = max(i, c0);
+  double* a = S + (size_t)i * ld + start;
+  double* b = packed + band_row_offset(i, c0, c1);
+  const int len = c1 - start;
+  if (to_packed) for (int k = threadIdx.x; k < len; k += 256) b[k] = a[k];
+  else for (int k = threadIdx.x; k < len; k += 256) a[k] = b[k];
+}
+void launch_pack_band(double* S, int32_t ld, int32_t n_rows, int32_t c0, int32_t c1, double* packed, bool to_packed,
+                      cudaStream_t s) {
+  const int rows = std::min(n_rows, c1);
+  if (rows <= 0 || c1 <= c0) return;
+  pack_band_kernel<<<rows, 256, 0, s>>>(S, ld, c0, c1, packed, to_packed);
   RCC_CUDA(cudaGetLastError());
 }
 

@@ -22,10 +22,10 @@ for name, kw in (("single", dict(n_markers=40, n_views=120, visibility=0.5, seed
     # system of 3-4 panels; the others take the automatic choice (replicated cuSOLVER at this size)
     if name.endswith("_dist"):
         os.environ["RCC_CHOLESKY"] = "dist"
-        os.environ["RCC_PACK_MIN_N"] = "0"          # and the packed-triangle all-reduce that goes with it
+        os.environ["RCC_SYRK_GROUPS"] = "3"         # and several bands in the overlapped reduction
     else:
         os.environ.pop("RCC_CHOLESKY", None)
-        os.environ.pop("RCC_PACK_MIN_N", None)
+        os.environ.pop("RCC_SYRK_GROUPS", None)
     scene = make_scene(kw.pop("n_markers"), kw.pop("n_views"), kw.pop("visibility"), **kw)
     opts = dict(max_iterations=30, function_tolerance=1e-14, gradient_tolerance=1e-12, parameter_tolerance=1e-13)
     dba = DistributedBA(scene, device=local)
@@ -47,7 +47,7 @@ if os.environ.get("RCC_CHECK_BIG") == "1":
     # is large enough for the automatic choice of the distributed Cholesky and the packed all-reduce
     from robot_camera_calibration_b200.scenes import config_scene
     os.environ.pop("RCC_CHOLESKY", None)
-    os.environ.pop("RCC_PACK_MIN_N", None)
+    os.environ.pop("RCC_SYRK_GROUPS", None)
     scene = config_scene(3, scale=0.1, blocked=True)
     dba = DistributedBA(scene, device=local, eliminate="views")
     p = dba.problem
