@@ -1,6 +1,7 @@
 """Multi-GPU plumbing: one process per GPU, observations sharded by the owner of
-their eliminated block, one all-reduce of the reduced system per LM iteration
-(SURVEY.md 8e).  `torch.distributed` is used only to bootstrap the NCCL
+their eliminated block; per LM iteration the library sums the reduced system over
+the ranks (band by band, behind its Schur kernel) and factors it with its block
+columns distributed over the ranks.  `torch.distributed` is used only to bootstrap the NCCL
 communicator that librcc_ba.so owns (broadcast of the 128-byte unique id) and
 to gather the eliminated-block parameters from their owners at the end.
 """
