@@ -17,7 +17,8 @@ value     = corner observations / s, whole job, inputs resident in HBM, L2 flush
 e2e       = same metric through the C ABI with HOST buffers: per step H2D of the pixel
             batch (int16, rcc_ba_update_pixels_i16) + all parameter blocks, linearize, D2H of cost + gradient.
 lm_iter   = seconds per full LM iteration (linearize + Schur + reduction over ranks + Cholesky solve +
-            back-substitution + candidate cost), max over ranks -- the strong-scaling curve.
+            back-substitution + candidate cost), max over ranks -- the strong-scaling curve.  lm_iter.cpu (N = 1) = the
+            same iteration on the host cores (C++/OpenMP restatement + LAPACK), see cpu_lm_iter().
 multi_gpu_parity (N>1) = N-rank vs 1-rank reduced system S, b and LM step on a small scene, run in this process;
             lm_iter.step_check = cost, model decrease, step norm and candidate cost of one LM step of the benchmarked
             problem: the problem is the same for every N, so these numbers must be too.
@@ -219,6 +220,55 @@ def cpu_baseline(cfg, scale, ranges, what, seconds=10.0):
                       "restatement of the Ceres evaluation + block normal equations (Ceres itself is not available), "
                       f"processed in {len(ranges)} view slice(s)",
             "s_per_pass": el / passes}
+
+
+def cpu_lm_iter(cfg, scale, radius=1e4, max_views=None, min_free_gb=48.0):
+    """Seconds per LM iteration of the CPU restatement (linearise -> block Schur complement -> dense Cholesky
+    [LAPACK through SciPy] -> back-substitution), the figure that stands beside `lm_iter`.  A workload of one view
+    slice (cfg2) is measured whole, second iteration of two.  A larger one (cfg4: a Schur complement of ~3 TFLOP,
+    minutes on the host, and a 30 009-unknown Cholesky) is measured on its FIRST slice of 250 keyframes -- whose
+    reduced system has the full size, so the dense solve is timed complete -- and the stages whose work is
+    proportional to the keyframes are scaled by the number of slices; the line says so."""
+    threads = len(os.sched_getaffinity(0))
+    if max_views is None:
+        max_views = {2: CONFIGS[2][1]}.get(cfg, CONFIGS[cfg][4])      # cfg2: the whole problem; else one generator chunk
+    ranges = slice_ranges(cfg, scale, max_views)
+    if len(ranges) > 1:
+        try:
+            import psutil
+            free = psutil.virtual_memory().available / 2 ** 30
+        except Exception:
+            free = None
+        if free is not None and free < min_free_gb:
+            return {"skipped": f"{free:.0f} GiB of host memory free, {min_free_gb:.0f} wanted for the dense reduced system"}
+    w = CpuWorkload(cfg, scale, ranges[:1], threads)
+    try:
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=threads)            # LAPACK's pool may have read torchrun's OMP_NUM_THREADS=1
+    except Exception:
+        limit = None
+    c = w.slices[0]
+    tm = {}
+    if len(ranges) == 1:
+        c.lm_iteration(radius)                                # warm-up: thread pools, page faults
+    else:
+        c.linearize()
+    t0 = time.perf_counter()
+    c.lm_iteration(radius, timings=tm)
+    measured = time.perf_counter() - t0
+    if limit is not None:
+        limit.restore_original_limits()
+    k = len(ranges)
+    est = k * (tm["linearize"] + tm["schur"] + tm["backsub"]) + tm["solve"]
+    what = ("the whole problem, one iteration after a warm-up iteration" if k == 1 else
+            f"keyframes {ranges[0][0]}..{ranges[0][1] - 1} of the workload ({4 * c.n} observations; its reduced "
+            f"system has the full size, so the dense solve is complete); linearise, Schur complement and "
+            f"back-substitution scaled by the {k} slices of the workload")
+    return {"s_per_iter": est, "measured_s": measured, "slices": k, "cores": w.threads, "kind": "port",
+            "stages_s": {kk: (k if kk != "solve" else 1) * v for kk, v in tm.items()},
+            "reduced_system_n": int(6 * c.n_f + c.ns), "sample": what,
+            "what": "C++/OpenMP restatement: Jet-autodiff linearisation, block Schur complement, LAPACK dpotrf/dpotrs "
+                    "(SciPy), back-substitution; same trust-region radius as lm_iter"}
 
 
 def run_reference(args):
@@ -560,6 +610,18 @@ def run_ours(args):
                             f"rank 0's shard of the workload (keyframes {ranges[0][0]}..{ranges[0][1] - 1})",
                             seconds=args.cpu_seconds)
 
+    # ... and the CPU seconds per LM iteration beside lm_iter (N = 1: LAPACK's thread pool is not pinned by torchrun)
+    lm_cpu = None
+    if world == 1 and not args.no_cpu_lm:
+        def guarded(cfg, scale):
+            try:
+                return cpu_lm_iter(cfg, scale)
+            except Exception as e:                       # the GPU line must not die with the CPU comparison
+                return {"error": repr(e)}
+        lm_cpu = guarded(args.config, args.scale)
+        if cfg2 is not None:
+            cfg2["lm_iter"]["cpu"] = guarded(2, 1.0)
+
     hbm_peak, peak_src = measured_peaks()
     fp64_peak = fp64_peak_tflops(local)
     prof, n_blocks = m["prof"], scene.n_blocks
@@ -618,7 +680,7 @@ def run_ours(args):
         "clocks": clocks,
         "lm_iter": {"s_per_iter": lm_ms_max * 1e-3, "obs_per_s": obs_all / (lm_ms_max * 1e-3),
                     "stage_ms_rank0": m["lm_prof"], "reduced_system_n": n_red, "n_pairs": n_pairs_all,
-                    "step_check": lm_check,
+                    "step_check": lm_check, "cpu": lm_cpu,
                     "what": "linearize + Schur + reduction over ranks + reduced solve + back-substitution + candidate "
                             "cost of the whole fixed problem; the strong-scaling curve is s_per_iter over N"},
         "stage_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[0] > 0},
@@ -653,6 +715,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the config's views (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="timed CPU work of the cpu_baseline leg")
     ap.add_argument("--no-cfg2", action="store_true", help="skip the cfg2 line at N=1")
+    ap.add_argument("--no-cpu-lm", action="store_true", help="skip the CPU seconds per LM iteration (lm_iter.cpu, N=1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,3 +39,18 @@ def test_strong_scaling_shards_tile_the_workload():
     assert np.array_equal(np.concatenate([p.views for p in parts]), full.views)
     assert sum(p.n_blocks for p in parts) == full.n_blocks
     assert all(np.array_equal(p.markers, full.markers) for p in parts)
+
+
+def test_cpu_lm_iteration_figure_of_the_bench():
+    """bench.py's lm_iter.cpu: measured whole for a one-slice workload; for a sliced one the stages proportional to the
+    keyframes are scaled by the slice count and the dense solve (full-size reduced system) counts once."""
+    import bench
+    whole = bench.cpu_lm_iter(2, 0.05)                               # 250 views, one slice
+    assert whole["slices"] == 1 and whole["reduced_system_n"] == 3009 and whole["kind"] == "port"
+    assert abs(whole["s_per_iter"] - sum(whole["stages_s"].values())) < 1e-12
+    assert 0 < whole["s_per_iter"] <= whole["measured_s"]
+    sliced = bench.cpu_lm_iter(2, 0.05, max_views=125, min_free_gb=0.5)
+    assert sliced["slices"] == 2 and sliced["reduced_system_n"] == 3009
+    st = sliced["stages_s"]
+    assert abs(sliced["s_per_iter"] - (st["linearize"] + st["schur"] + st["backsub"] + st["solve"])) < 1e-12
+    assert "scaled by the 2 slices" in sliced["sample"]
