@@ -392,6 +392,166 @@ __global__ void __launch_bounds__(SY_WARPS * 32, RCC_SY_CTAS) schur_syrk_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------
+// schur_syrk (v3, register accumulators): same CTA = (block row f, column tile J) and the same staging of the
+// pairs (e, f) of column f as v2, but the warp's 6 x 192 strip of S lives in REGISTERS: lane l owns the columns
+// l, l + 32, ..., l + 160 of the warp's 32-block sub-tile (6 columns x 6 rows = 36 accumulators).  For a pair
+// (e, f) a 32-bit presence mask of row e over the sub-tile (tile_mask) tells every lane whether the block its
+// column sits in is a partner, and tile_ptr + popcount of the mask below it is that partner's pair index: the lane
+// loads its 48-byte column of Y_ef' (a zero column when the block is absent) -- all six columns of a visit are in
+// flight together -- and adds Y_ef^T y to its accumulators.  No shared-memory read-modify-write, no ordering
+// between lanes, one store of the strip at the end; a 32-column window none of whose blocks is present is skipped.
+// Lanes whose block is absent do no useful work (the price: FP64 issue slots at the density of the rows), which
+// pays off when rows are dense enough that v2's accumulator traffic through shared memory is the limit.
+// Fixed summation order (ascending e) -> bitwise reproducible.
+// ---------------------------------------------------------------------------
+constexpr int SR_WARPS = SY_WARPS * SY_G;   // one 32-block sub-tile per warp, the CTA covers the same column tile as v2
+constexpr int SR_BATCH = 32;
+#ifndef RCC_SR_PASS
+#define RCC_SR_PASS 3    // columns of a lane whose partner loads are in flight together: 6 (one pass, ~250 registers) or 3
+#endif
+#ifndef RCC_SR_CTAS
+#define RCC_SR_CTAS (RCC_SR_PASS == 6 ? 4 : 6)
+#endif
+constexpr int SR_PASS = RCC_SR_PASS;
+static_assert(6 % SR_PASS == 0, "passes must tile the six columns of a lane");
+__device__ __align__(16) double sr_zero_column[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+// blocks of the sub-tile that the 32 columns 32 j .. 32 j + 31 touch
+__host__ __device__ constexpr unsigned sr_window(int j) {
+  const int b0 = (32 * j) / 6, b1 = (32 * j + 31) / 6;
+  return (b1 >= 31 ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
+}
+
+__global__ void __launch_bounds__(SR_WARPS * 32, RCC_SR_CTAS) schur_syrk_reg_kernel(const SchurSyrkArgs a) {
+  __shared__ __align__(16) double yi[2][SR_BATCH * 36];   // staged Y_ef of the batch, double buffered
+  const int f = a.cta_list[2 * blockIdx.x];
+  const int J = a.cta_list[2 * blockIdx.x + 1];
+  const int sub_of_f = f >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int js = J * SR_WARPS + warp;                 // this warp's sub-tile
+  const bool active = (js >= sub_of_f) && (js < a.n_tiles);
+  const int subbase = js * 32;
+  const int c0 = a.col_ptr[f], c1 = a.col_ptr[f + 1];
+  const int tps = a.n_tiles + 1;
+  // the diagonal sub-tile only takes partners f' >= f
+  const unsigned keep = (js == sub_of_f) ? ~((1u << (f & 31)) - 1u) : 0xffffffffu;
+  int blk[6], colo[6];                                // block (0..31) and column in the block of this lane's columns
+  unsigned below[6];                                  // bits of the blocks before it
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int c = lane + 32 * j;
+    blk[j] = c / 6;
+    colo[j] = (c - blk[j] * 6) * 6;                   // offset of the column inside a 36-double block
+    below[j] = (1u << blk[j]) - 1u;
+  }
+  double acc[6][6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) acc[j][r] = 0.0;
+
+  auto stage = [&](int cb, int buf) {
+    const int nb = min(SR_BATCH, c1 - cb);
+    double2* dst = reinterpret_cast<double2*>(yi[buf]);
+    for (int k = tid; k < nb * 18; k += SR_WARPS * 32) {
+      const int q = k / 18, piece = k - q * 18;
+      const int p = a.col_pair[cb + q];
+      sy_cp_async16(dst + k, reinterpret_cast<const double2*>(a.Y + (size_t)p * 36) + piece);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // lane q of every warp: presence mask and first pair of row e_q inside the warp's sub-tile
+  auto meta = [&](int cb, unsigned& mask, int& base) {
+    mask = 0u;
+    base = 0;
+    if (active && cb + lane < c1) {
+      const int e = a.pair_e[a.col_pair[cb + lane]];
+      mask = a.tile_mask[(size_t)e * a.n_tiles + js];
+      base = a.tile_ptr[(size_t)e * tps + js];
+    }
+  };
+
+  unsigned mask_cur, mask_nxt = 0u;
+  int base_cur, base_nxt = 0;
+  if (c0 < c1) stage(c0, 0);
+  meta(c0, mask_cur, base_cur);
+  int buf = 0;
+  for (int cb = c0; cb < c1; cb += SR_BATCH, buf ^= 1) {
+    const int nb = min(SR_BATCH, c1 - cb);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // batch `cb` staged by everyone; batch `cb - SR_BATCH` consumed by everyone
+    if (cb + SR_BATCH < c1) {
+      stage(cb + SR_BATCH, buf ^ 1);
+      meta(cb + SR_BATCH, mask_nxt, base_nxt);
+    }
+    if (active) {
+      for (int q = 0; q < nb; ++q) {
+        const unsigned mfull = __shfl_sync(0xffffffffu, mask_cur, q);
+        const unsigned m = mfull & keep;
+        if (m == 0u) continue;                         // warp-uniform
+        const int base = __shfl_sync(0xffffffffu, base_cur, q);
+        const double2* yq = reinterpret_cast<const double2*>(yi[buf] + q * 36);   // Y_ef: yq[3 r + i] = rows 2i, 2i+1 of column r
+        // SR_PASS columns of the lane per pass: their partner columns (or the zero column) are in flight together,
+        // then Y_ef^T y is added row by row (Y_ef comes from the staged copy, broadcast)
+#pragma unroll
+        for (int j0 = 0; j0 < 6; j0 += SR_PASS) {
+          unsigned win = 0u;
+#pragma unroll
+          for (int j = j0; j < j0 + SR_PASS; ++j) win |= sr_window(j);
+          if (!(m & win)) continue;                      // warp-uniform
+          double2 y[SR_PASS][3];
+#pragma unroll
+          for (int jj = 0; jj < SR_PASS; ++jj) {
+            const int j = j0 + jj;
+            // pair index of the lane's block in row e = first pair of the sub-tile + partners below it (32-bit
+            // offsets: the launcher checks 36 n_pairs < 2^32); absent block -> the zero column
+            const unsigned off = (unsigned)(base + __popc(mfull & below[j])) * 36u + (unsigned)colo[j];
+            const double2* yp = ((m >> blk[j]) & 1u) ? reinterpret_cast<const double2*>(a.Y + off)
+                                                     : reinterpret_cast<const double2*>(sr_zero_column);
+            y[jj][0] = yp[0];
+            y[jj][1] = yp[1];
+            y[jj][2] = yp[2];
+          }
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const double2 a0 = yq[3 * r], a1 = yq[3 * r + 1], a2 = yq[3 * r + 2];
+#pragma unroll
+            for (int jj = 0; jj < SR_PASS; ++jj) {
+              const int j = j0 + jj;
+              if (m & sr_window(j)) {                    // warp-uniform
+                double t = acc[j][r];
+                t = fma(a0.x, y[jj][0].x, t);
+                t = fma(a0.y, y[jj][0].y, t);
+                t = fma(a1.x, y[jj][1].x, t);
+                t = fma(a1.y, y[jj][1].y, t);
+                t = fma(a2.x, y[jj][2].x, t);
+                t = fma(a2.y, y[jj][2].y, t);
+                acc[j][r] = t;
+              }
+            }
+          }
+        }
+      }
+    }
+    mask_cur = mask_nxt;
+    base_cur = base_nxt;
+  }
+  // S strip = base - acc   (upper triangle in block granularity); a warp-wide store is 32 consecutive columns
+  if (!active) return;
+  const size_t row0 = (size_t)6 * f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int fp = subbase + blk[j];
+    if (fp >= a.n_f || fp < f) continue;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double base = 0.0;
+      if (fp == f) base = a.Hff[(size_t)f * 36 + r * 6 + colo[j] / 6];
+      a.S[(row0 + r) * a.ld + (size_t)6 * subbase + lane + 32 * j] = base - acc[j][r];
+    }
+  }
+}
+
 // border strip of block row f:  [H_fs | g_f] - sum_e Y_ef^T Yb_e.  Every pair of column f meets every
 // border block, so a lane owns fixed border columns and keeps their 6-row outputs in registers:
 // lane = (slot u, column); the (warp, slot) slices stride over the staged pairs and are summed in a
@@ -496,7 +656,15 @@ void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)(SY_WARPS * SY_SUB * 36 + 2 * SY_BATCH * 36) * sizeof(double);
   static SmemOptIn optin;
   optin.ensure(schur_syrk_kernel, smem);
-  if (a.n_ctas > 0) schur_syrk_kernel<<<a.n_ctas, SY_WARPS * 32, smem, s>>>(a);
+  if (a.n_ctas > 0) {
+    if (a.variant == 1) {
+      RCC_REQUIRE(a.tile_mask != nullptr, RCC_BAD_ARG, "schur_syrk: the register variant needs the presence masks");
+      RCC_REQUIRE(a.n_pairs36_fits_u32, RCC_BAD_ARG, "schur_syrk: the register variant indexes Y with 32-bit offsets");
+      schur_syrk_reg_kernel<<<a.n_ctas, SR_WARPS * 32, 0, s>>>(a);
+    } else {
+      schur_syrk_kernel<<<a.n_ctas, SY_WARPS * 32, smem, s>>>(a);
+    }
+  }
   RCC_CUDA(cudaGetLastError());
 }
 
