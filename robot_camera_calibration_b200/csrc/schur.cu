@@ -212,6 +212,12 @@ constexpr int SY_G = SY_SUB / 32;    // tile_ptr entries per warp sub-tile
 #ifndef RCC_SY_PF
 #define RCC_SY_PF 1      // prefetch depth of the partner-column loads, in 32-item steps
 #endif
+#ifndef RCC_SY_COLS
+#define RCC_SY_COLS 1    // columns of a partner block per lane item (1, 2 or 3): fatter items = fewer 32-item steps per pair
+#endif
+constexpr int SY_COLS = RCC_SY_COLS;
+constexpr int SY_IPB = 6 / SY_COLS;      // items per partner block
+static_assert(6 % SY_COLS == 0, "items must tile the six columns of a block");
 constexpr int SY_BATCH = RCC_SY_BATCH;   // pairs of column f staged per round (<= 32: one lane per pair holds its range)
 static_assert(SY_BATCH <= 32, "a batch must fit the lanes of a warp");
 static_assert(SY_SUB % 32 == 0, "warp sub-tile must be a multiple of the tile_ptr granularity");
@@ -230,24 +236,23 @@ __device__ __forceinline__ bool sy_advance(SyCursor& c, int nb, int lo_lane, int
   while (c.base >= c.n_items) {
     if (++c.q >= nb) return false;
     c.lo = __shfl_sync(0xffffffffu, lo_lane, c.q);
-    c.n_items = (__shfl_sync(0xffffffffu, hi_lane, c.q) - c.lo) * 6;
+    c.n_items = (__shfl_sync(0xffffffffu, hi_lane, c.q) - c.lo) * SY_IPB;
     c.base = 0;
   }
   return true;
 }
 // one lane's item of a step: column c of partner block Y_ef' and its slot in the warp's output slice
-struct SyItem { double2 y0, y1, y2; int pf, col; };   // pf < 0: idle lane.  (raw loads only: nothing here waits on memory)
+struct SyItem { double2 y[3 * SY_COLS]; int pf, col; };   // pf < 0: idle lane.  (raw loads only: nothing here waits on memory)
 __device__ __forceinline__ void sy_load(const SchurSyrkArgs& a, const SyCursor& c, int lane, int subbase, SyItem& it) {
   const int idx = c.base + lane;
   it.pf = -1;
   it.col = 0;
   if (idx < c.n_items) {
-    const int jj = idx / 6, col = idx - jj * 6;
+    const int jj = idx / SY_IPB, col = (idx - jj * SY_IPB) * SY_COLS;
     const int j = c.lo + jj;
     const double2* yp = reinterpret_cast<const double2*>(a.Y + (size_t)j * 36 + col * 6);
-    it.y0 = yp[0];
-    it.y1 = yp[1];
-    it.y2 = yp[2];
+#pragma unroll
+    for (int i = 0; i < 3 * SY_COLS; ++i) it.y[i] = yp[i];
     it.pf = a.pair_f[j];
     it.col = col;
   }
@@ -343,23 +348,27 @@ __global__ void __launch_bounds__(SY_WARPS * 32, RCC_SY_CTAS) schur_syrk_kernel(
           q_loaded = cur.q;
         }
         if (it_c.pf >= 0) {
-          double v[6];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            double t = Yi[r * 6] * it_c.y0.x;
-            t = fma(Yi[r * 6 + 1], it_c.y0.y, t);
-            t = fma(Yi[r * 6 + 2], it_c.y1.x, t);
-            t = fma(Yi[r * 6 + 3], it_c.y1.y, t);
-            t = fma(Yi[r * 6 + 4], it_c.y2.x, t);
-            t = fma(Yi[r * 6 + 5], it_c.y2.y, t);
-            v[r] = t;
-          }
           double2* ap = reinterpret_cast<double2*>(acc + (it_c.pf - subbase) * 36 + it_c.col * 6);
-          double2 a0 = ap[0], a1 = ap[1], a2 = ap[2];
-          a0.x += v[0]; a0.y += v[1];
-          a1.x += v[2]; a1.y += v[3];
-          a2.x += v[4]; a2.y += v[5];
-          ap[0] = a0; ap[1] = a1; ap[2] = a2;
+#pragma unroll
+          for (int cc = 0; cc < SY_COLS; ++cc) {
+            const double2 y0 = it_c.y[3 * cc], y1 = it_c.y[3 * cc + 1], y2 = it_c.y[3 * cc + 2];
+            double v[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              double t = Yi[r * 6] * y0.x;
+              t = fma(Yi[r * 6 + 1], y0.y, t);
+              t = fma(Yi[r * 6 + 2], y1.x, t);
+              t = fma(Yi[r * 6 + 3], y1.y, t);
+              t = fma(Yi[r * 6 + 4], y2.x, t);
+              t = fma(Yi[r * 6 + 5], y2.y, t);
+              v[r] = t;
+            }
+            double2 a0 = ap[3 * cc], a1 = ap[3 * cc + 1], a2 = ap[3 * cc + 2];
+            a0.x += v[0]; a0.y += v[1];
+            a1.x += v[2]; a1.y += v[3];
+            a2.x += v[4]; a2.y += v[5];
+            ap[3 * cc] = a0; ap[3 * cc + 1] = a1; ap[3 * cc + 2] = a2;
+          }
         }
         __syncwarp();   // the next pair may touch the same output columns from other lanes
         cur = nxt;
