@@ -198,7 +198,7 @@ struct SchurSyrkArgs {
   const int32_t* pair_f;         // [n_pairs]
   const int32_t* tile_ptr;       // [n_e*(n_tiles+1)]
   const uint32_t* tile_mask;     // [n_e*n_tiles] bit b of [e][J]: row e has a pair with f = 32 J + b
-  int32_t variant;               // 0: v2 (accumulators in shared memory), 1: v3 (accumulators in registers)
+  int32_t variant;               // 0: v2 (accumulators in shared memory), 1: v3 (accumulators in registers), 2: v4 (v2 with a tensor-core product)
   int32_t n_pairs36_fits_u32;    // 36 n_pairs < 2^32 (v3 indexes Y with 32-bit offsets)
   const int32_t* cta_list;       // [n_ctas][2] (f, column tile) of schur_syrk_kernel, heaviest first
   int32_t n_ctas;

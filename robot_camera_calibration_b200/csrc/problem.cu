@@ -464,6 +464,7 @@ static void build_indices(P_t* P, const int32_t* view_idx, const int32_t* marker
       const char* v = getenv("RCC_SYRK");
       if (v && !strcmp(v, "v2")) P->syrk_variant = 0;
       if (v && !strcmp(v, "v3")) P->syrk_variant = 1;
+      if (v && !strcmp(v, "v4")) P->syrk_variant = 2;
     }
     // work list of the SYRK: one CTA per (block row f, column tile J on or right of the diagonal),
     // column tile major so that co-resident CTAs read the same columns of Y (L2 locality; a
@@ -666,7 +667,7 @@ static void do_schur(P_t* P, double radius) {
     a.cta_list = P->syrk_ctas.p; a.n_ctas = P->n_syrk_ctas;
     a.tile_mask = P->tile_mask.p;
     a.n_pairs36_fits_u32 = (uint64_t)P->n_pairs * 36 < ((uint64_t)1 << 32);
-    a.variant = (P->tile_mask.p && a.n_pairs36_fits_u32) ? P->syrk_variant : 0;
+    a.variant = (P->syrk_variant == 1 && !(P->tile_mask.p && a.n_pairs36_fits_u32)) ? 0 : P->syrk_variant;
     a.tile_ptr = P->tile_ptr.p; a.Y = P->Y.p; a.Yb = P->Yb.p; a.Hff = P->Hff.p; a.gf = P->gf.p; a.Hfs = P->Hfs.p;
     a.S = P->S.p;
     RCC_CUDA(cudaEventRecord(P->ev_fork, P->stream));

@@ -91,7 +91,7 @@ struct rcc_ba_problem {
   int f_piece_ptr[PIX_PIECES + 1] = {0};
   rcc::DBuf<int32_t> row_ptr, pair_e, pair_f, pair_mptr, pair_members, row_pos0, col_ptr, col_pair, tile_ptr, syrk_ctas, e_count;
   rcc::DBuf<uint32_t> tile_mask;   // [n_e][n_tiles] presence bits of row e inside a 32-block column sub-tile (SYRK v3)
-  int syrk_variant = 0;            // 0: v2 (shared-memory accumulators), 1: v3 (register accumulators); RCC_SYRK=v2|v3
+  int syrk_variant = 0;            // 0: v2 (shared-memory accumulators), 1: v3 (register accumulators), 2: v4 (v2 + DMMA product); RCC_SYRK=v2|v3|v4
   rcc::DBuf<uint8_t> e_const;
 
   // linearisation products

@@ -561,6 +561,179 @@ __global__ void __launch_bounds__(SR_WARPS * 32, RCC_SR_CTAS) schur_syrk_reg_ker
   }
 }
 
+// ---------------------------------------------------------------------------
+// schur_syrk (v4, tensor-core product): same CTA = (block row f, column tile J), same staging of the pairs (e, f) of
+// column f and the same per-warp accumulator slice in shared memory as v2, but the product of a visit is formed by the
+// FP64 tensor cores.  The partner blocks of row e inside the warp's sub-tile are CONSECUTIVE pairs, i.e. their
+// column-major 6 x 6 records are one contiguous 6 x (6 n_p) panel P of Y; O = Y_ef^T P is computed 8 columns at a
+// time with mma.m8n8k4 (A = Y_ef^T padded to 8 x 8: one register per lane and k-step instead of v2's 36 broadcast
+// registers, B = 8 columns of P read straight from global memory, two k-steps for the 6 rows) and the 6 x 8 result
+// fragment is added to the slice (layout [block][row][column]: a lane's two results are one 16-byte access).
+// What this saves over v2 is shared-memory traffic -- no re-read of Y_ef per (pair, sub-tile), which is 36 of v2's
+// ~95 wavefronts per visit -- and instructions; what it costs is FP64 pipe time (8 x 8 x 8 executed for 6 x 8 x 6).
+// Fixed order (ascending e, column groups in order) -> bitwise reproducible.
+// ---------------------------------------------------------------------------
+constexpr int SM_WARPS = SY_WARPS * SY_G;   // one 32-block sub-tile per warp; the CTA covers the same column tile as v2
+constexpr int SM_BATCH = 32;
+constexpr int SM_CHUNK = 6;                 // column groups of a visit whose B fragments are loaded together
+
+// D(8x8) += A(8x4) B(4x8), FP64.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4)], D[l/4][2(l%4)+1].
+__device__ __forceinline__ void sm_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+struct SmVisit {
+  const double* Yp;   // panel of the partner blocks: column col of the panel at Yp + 6 col
+  int ncol;           // 6 x partners (0: nothing to do)
+  int ngrp;           // column groups of 8
+  int pf_lane;        // lane i < partners: position of partner i in the warp's slice
+  double a0, a1;      // A fragments (Y_ef^T) of the two k-steps
+};
+// B fragments of the column groups cg0 .. cg0 + SM_CHUNK - 1: lane (g = l/4, t = l%4) holds P[t][8 cg + g] and P[4 + t][..]
+__device__ __forceinline__ void sm_load(const SmVisit& v, int cg0, int g, int t, double (&b0)[SM_CHUNK], double (&b1)[SM_CHUNK]) {
+#pragma unroll
+  for (int i = 0; i < SM_CHUNK; ++i) {
+    const int col = 8 * (cg0 + i) + g;
+    const bool ok = col < v.ncol;
+    b0[i] = ok ? v.Yp[col * 6 + t] : 0.0;
+    b1[i] = (ok && t < 2) ? v.Yp[col * 6 + 4 + t] : 0.0;
+  }
+}
+__device__ __forceinline__ void sm_compute(const SmVisit& v, int cg0, int g, int t, const double (&b0)[SM_CHUNK],
+                                           const double (&b1)[SM_CHUNK], double* acc) {
+#pragma unroll
+  for (int i = 0; i < SM_CHUNK; ++i) {
+    const int cg = cg0 + i;
+    if (cg < v.ngrp) {                                   // warp-uniform
+      double d[2] = {0.0, 0.0};
+      sm_dmma(d, v.a0, b0[i]);
+      sm_dmma(d, v.a1, b1[i]);
+      const int col = 8 * cg + 2 * t;                    // the lane holds O[g][col], O[g][col + 1]: same partner block
+      const int jj = col / 6, c = col - 6 * jj;
+      const int pfl = __shfl_sync(0xffffffffu, v.pf_lane, jj & 31);
+      if (g < 6 && col < v.ncol) {
+        double2* ap = reinterpret_cast<double2*>(acc + pfl * 36 + g * 6 + c);
+        double2 w = *ap;
+        w.x += d[0];
+        w.y += d[1];
+        *ap = w;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SM_WARPS * 32, 6) schur_syrk_mma_kernel(const SchurSyrkArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int f = a.cta_list[2 * blockIdx.x];
+  const int J = a.cta_list[2 * blockIdx.x + 1];
+  const int sub_of_f = f >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  double* acc = sm + warp * (32 * 36);                // [32 blocks][6 rows][6 columns]
+  double* yi = sm + SM_WARPS * 32 * 36;               // [2][SM_BATCH][36] staged Y_ef
+  for (int k = lane; k < 32 * 36; k += 32) acc[k] = 0.0;
+
+  const int js = J * SM_WARPS + warp;                 // this warp's sub-tile
+  const bool active = (js >= sub_of_f) && (js < a.n_tiles);
+  const int subbase = js * 32;
+  const int c0 = a.col_ptr[f], c1 = a.col_ptr[f + 1];
+  const int tps = a.n_tiles + 1;
+
+  auto stage = [&](int cb, int buf) {
+    const int nb = min(SM_BATCH, c1 - cb);
+    double2* dst = reinterpret_cast<double2*>(yi + buf * SM_BATCH * 36);
+    for (int k = tid; k < nb * 18; k += SM_WARPS * 32) {
+      const int q = k / 18, piece = k - q * 18;
+      const int p = a.col_pair[cb + q];
+      sy_cp_async16(dst + k, reinterpret_cast<const double2*>(a.Y + (size_t)p * 36) + piece);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // lane q of every warp: partner range of pair q of the batch inside the warp's sub-tile
+  auto meta = [&](int cb, int& lo, int& hi) {
+    lo = 0;
+    hi = 0;
+    if (active && cb + lane < c1) {
+      const int p = a.col_pair[cb + lane];
+      const int* tp = a.tile_ptr + (size_t)a.pair_e[p] * tps;
+      lo = (js == sub_of_f) ? p : tp[js];
+      hi = tp[js + 1];
+    }
+  };
+  // everything a visit needs except the B fragments (q >= nb or no partner: ncol = 0)
+  auto setup = [&](int q, int nb, int lo_lane, int hi_lane, const double* ybuf, SmVisit& v) {
+    const int qq = min(q, nb - 1);
+    const int lo = __shfl_sync(0xffffffffu, lo_lane, qq);
+    const int hi = __shfl_sync(0xffffffffu, hi_lane, qq);
+    const int np = (q < nb) ? max(hi - lo, 0) : 0;
+    v.ncol = 6 * np;
+    v.ngrp = (v.ncol + 7) >> 3;
+    v.Yp = a.Y + (size_t)lo * 36;
+    v.pf_lane = (lane < np) ? a.pair_f[lo + lane] - subbase : 0;
+    const double* yb = ybuf + qq * 36;                  // Y_ef: element (k, r) at yb[6 r + k]
+    v.a0 = (g < 6) ? yb[g * 6 + t] : 0.0;
+    v.a1 = (g < 6 && t < 2) ? yb[g * 6 + 4 + t] : 0.0;
+  };
+  auto rest = [&](const SmVisit& v) {                  // column groups beyond the first chunk (rows with > 8 partners)
+    for (int cg0 = SM_CHUNK; cg0 < v.ngrp; cg0 += SM_CHUNK) {
+      double b0[SM_CHUNK], b1[SM_CHUNK];
+      sm_load(v, cg0, g, t, b0, b1);
+      sm_compute(v, cg0, g, t, b0, b1, acc);
+    }
+  };
+
+  int lo_cur, hi_cur, lo_nxt = 0, hi_nxt = 0;
+  if (c0 < c1) stage(c0, 0);
+  meta(c0, lo_cur, hi_cur);
+  int buf = 0;
+  for (int cb = c0; cb < c1; cb += SM_BATCH, buf ^= 1) {
+    const int nb = min(SM_BATCH, c1 - cb);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // batch `cb` staged by everyone; batch `cb - SM_BATCH` consumed by everyone
+    if (cb + SM_BATCH < c1) {
+      stage(cb + SM_BATCH, buf ^ 1);
+      meta(cb + SM_BATCH, lo_nxt, hi_nxt);
+    }
+    if (active) {
+      const double* ybuf = yi + buf * SM_BATCH * 36;
+      // two pairs per round: the loads of both are issued before the first is computed
+      for (int q = 0; q < nb; q += 2) {
+        SmVisit v0, v1;
+        setup(q, nb, lo_cur, hi_cur, ybuf, v0);
+        setup(q + 1, nb, lo_cur, hi_cur, ybuf, v1);
+        double b00[SM_CHUNK], b01[SM_CHUNK], b10[SM_CHUNK], b11[SM_CHUNK];
+        sm_load(v0, 0, g, t, b00, b01);
+        sm_load(v1, 0, g, t, b10, b11);
+        sm_compute(v0, 0, g, t, b00, b01, acc);
+        rest(v0);
+        __syncwarp();   // the next pair may touch the same outputs from other lanes
+        sm_compute(v1, 0, g, t, b10, b11, acc);
+        rest(v1);
+        __syncwarp();
+      }
+    }
+    lo_cur = lo_nxt;
+    hi_cur = hi_nxt;
+  }
+  // S strip = base - acc   (upper triangle in block granularity), rows written as contiguous runs
+  if (!active) return;
+  __syncwarp();
+  const int nblk = min(32, a.n_f - subbase);
+  const size_t row0 = (size_t)6 * f;
+  for (int r = 0; r < 6; ++r) {
+    for (int cl = lane; cl < nblk * 6; cl += 32) {
+      const int fl = cl / 6, c = cl - fl * 6;
+      const int fp = subbase + fl;
+      if (fp < f) continue;
+      double base = 0.0;
+      if (fp == f) base = a.Hff[(size_t)f * 36 + r * 6 + c];
+      a.S[(row0 + r) * a.ld + (size_t)6 * subbase + cl] = base - acc[fl * 36 + r * 6 + c];
+    }
+  }
+}
+
 // border strip of block row f:  [H_fs | g_f] - sum_e Y_ef^T Yb_e.  Every pair of column f meets every
 // border block, so a lane owns fixed border columns and keeps their 6-row outputs in registers:
 // lane = (slot u, column); the (warp, slot) slices stride over the staged pairs and are summed in a
@@ -666,7 +839,12 @@ void launch_schur_syrk(const SchurSyrkArgs& a, cudaStream_t s) {
   static SmemOptIn optin;
   optin.ensure(schur_syrk_kernel, smem);
   if (a.n_ctas > 0) {
-    if (a.variant == 1) {
+    if (a.variant == 2) {
+      const size_t smem4 = (size_t)(SM_WARPS * 32 * 36 + 2 * SM_BATCH * 36) * sizeof(double);
+      static SmemOptIn optin4;
+      optin4.ensure(schur_syrk_mma_kernel, smem4);
+      schur_syrk_mma_kernel<<<a.n_ctas, SM_WARPS * 32, smem4, s>>>(a);
+    } else if (a.variant == 1) {
       RCC_REQUIRE(a.tile_mask != nullptr, RCC_BAD_ARG, "schur_syrk: the register variant needs the presence masks");
       RCC_REQUIRE(a.n_pairs36_fits_u32, RCC_BAD_ARG, "schur_syrk: the register variant indexes Y with 32-bit offsets");
       schur_syrk_reg_kernel<<<a.n_ctas, SR_WARPS * 32, 0, s>>>(a);
