@@ -129,3 +129,30 @@ def test_missing_intrinsics_or_targets_are_errors_and_integer_corners_stay_integ
         f.write("targets:\n")
     with pytest.raises(ValueError):
         io_yaml.read_dataset(str(tmp_path), intr=s.intr[0], dist=s.dist[0])
+
+
+def test_command_line_help_and_dataset_errors(tmp_path, capsys):
+    """python -m robot_camera_calibration_b200 <detections directory>: argument parsing, and a dataset without
+    camera.yaml is refused (exit code 2) before any device is touched."""
+    from robot_camera_calibration_b200.__main__ import main, parser
+    a = parser().parse_args([str(tmp_path), "--fix-intrinsics", "--max-iterations", "7"])
+    assert a.fix_intrinsics and a.max_iterations == 7 and a.device == 0
+    s = make_scene(6, 5, 0.9, seed=92, round_pixels=True)
+    io_yaml.write_dataset(str(tmp_path), s)
+    os.remove(os.path.join(str(tmp_path), "camera.yaml"))
+    assert main([str(tmp_path)]) == 2
+    assert "camera.yaml" in capsys.readouterr().err
+
+
+@pytest.mark.gpu
+def test_command_line_runs_milestone_3(tmp_path, capsys):
+    import json
+    from robot_camera_calibration_b200.__main__ import main
+    s = make_scene(10, 25, 0.8, seed=8, pixel_noise=0.0, perturb=(0.01, 0.01, 0.0))
+    io_yaml.write_dataset(str(tmp_path), s)
+    before, _, _ = io_yaml.read_dataset(str(tmp_path))
+    assert main([str(tmp_path), "--fix-intrinsics", "--precision", "repr", "--max-iterations", "40"]) == 0
+    summ = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert summ["final_cost"] < 0.2 * summ["initial_cost"] and summ["termination_name"] != "failure"
+    after, _, _ = io_yaml.read_dataset(str(tmp_path))
+    assert np.abs(after.markers - s.truth["markers"]).mean() < np.abs(before.markers - s.truth["markers"]).mean()
